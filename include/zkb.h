@@ -1,0 +1,148 @@
+/* zkb.h — C ABI of the B200-native Groth16 proving backend (libzkb200.so).
+ *
+ * This is the drop-in boundary for ZoKrates' proving hot path.  A `zokrates_b200` Rust crate
+ * implementing `zokrates_proof_systems::Backend<T, G16>` binds exactly these entry points through
+ * `extern "C"` (see INTEGRATION.md for the bindgen-style stub and the CLI patch); the Python host
+ * mirror in zokrates_b200/backend.py binds the same symbols with ctypes.
+ *
+ * Conventions
+ *   - every function returns an int32 status (ZKB_OK = 0); zkb_last_error() gives the message of the
+ *     last failure on the calling thread.  Nothing throws or aborts across this boundary; the
+ *     reference panics on failure (zokrates_ark/src/groth16.rs:42,44), the shim turns a non-zero
+ *     status into the same panic.
+ *   - the caller owns every buffer; the callee copies what it needs before returning.
+ *   - field elements cross the boundary as canonical little-endian bytes, exactly what
+ *     `Field::write` / ark `CanonicalSerialize` produce (zokrates_field/src/lib.rs:215-233).
+ *   - one context drives one GPU (one process per GPU); multi-GPU proving shards every MSM by index
+ *     range (`rank`, `world` at zkb_pk_load) and exchanges 5 partial sums per proof.
+ *   - there is no CPU fallback: without a usable CUDA device zkb_ctx_create fails with ZKB_E_CUDA.
+ */
+#ifndef ZKB_H
+#define ZKB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZKB_OK 0
+#define ZKB_E_ARG 1
+#define ZKB_E_FORMAT 2
+#define ZKB_E_CUDA 3
+#define ZKB_E_OOM 4
+#define ZKB_E_UNSAT 5
+#define ZKB_E_INTERNAL 6
+
+/* curve ids: the curves of BASELINE.json; names as zokrates_field `Field::name()`
+ * (zokrates_field/src/bn128.rs:1-13, bls12_381.rs:1-13) */
+#define ZKB_CURVE_BN128 0
+#define ZKB_CURVE_BLS12_381 1
+
+typedef struct zkb_ctx zkb_ctx;
+
+const char* zkb_last_error(void);
+/* ABI version of this header */
+uint32_t zkb_abi_version(void);
+/* number of CUDA devices visible; <0 on CUDA failure */
+int32_t zkb_device_count(void);
+
+/* Replaces the implicit global state of the reference's static `Backend` methods
+ * (zokrates_proof_systems/src/lib.rs:98-112 have no `self`): the Rust shim keeps one lazily
+ * created context per (curve, device). */
+int32_t zkb_ctx_create(int32_t curve, int32_t device, zkb_ctx** out);
+void zkb_ctx_destroy(zkb_ctx* ctx);
+
+/* Sizes in bytes for `curve`: out[0] = |Fr|, out[1] = |Fq|, out[2] = proof bytes (8 |Fq|),
+ * out[3] = partial-sum blob bytes (zkb_groth16_prove_partial). */
+int32_t zkb_curve_sizes(int32_t curve, uint64_t out[4]);
+
+/* ---- proving key ------------------------------------------------------------------------------
+ * pk_bytes: exactly what ark's `ProvingKey::serialize_unchecked` wrote, i.e. the `proving.key`
+ * file (zokrates_ark/src/groth16.rs:97-98; read back unchecked at :40-42; layout SURVEY.md A.3).
+ * rank/world: this context keeps the [rank/world) index slice of every query vector resident in
+ * HBM (world = 1 for single-GPU). */
+int32_t zkb_pk_load(zkb_ctx* ctx, const uint8_t* pk_bytes, size_t len, uint32_t rank, uint32_t world,
+                    uint64_t* pk_handle);
+/* out[0]=gamma_abc len (= instance count incl. one), out[1]=a_query len (= variables), out[2]=h_query len,
+ * out[3]=l_query len */
+int32_t zkb_pk_info(zkb_ctx* ctx, uint64_t pk_handle, uint64_t out[4]);
+int32_t zkb_pk_free(zkb_ctx* ctx, uint64_t pk_handle);
+
+/* ---- R1CS -------------------------------------------------------------------------------------
+ * Matrices A, B, C in CSR form with columns in ark-relations order (0 = one, then instance
+ * variables, then witness variables — the order `Computation::generate_constraints` allocates,
+ * zokrates_ark/src/lib.rs:80-130).  Coefficients canonical LE, 4 x u64 each. */
+int32_t zkb_r1cs_load(zkb_ctx* ctx, uint64_t n_constraints, uint64_t n_instance /* incl. one */,
+                      uint64_t n_witness,
+                      const uint64_t* a_rowptr, const uint32_t* a_col, const uint64_t* a_val,
+                      const uint64_t* b_rowptr, const uint32_t* b_col, const uint64_t* b_val,
+                      const uint64_t* c_rowptr, const uint32_t* c_col, const uint64_t* c_val,
+                      uint64_t* r1cs_handle);
+int32_t zkb_r1cs_free(zkb_ctx* ctx, uint64_t r1cs_handle);
+
+/* ---- Groth16 prover ---------------------------------------------------------------------------
+ * Replaces `Groth16::<E>::prove(&pk, computation, rng)` (zokrates_ark/src/groth16.rs:44).
+ * z: full assignment [1, instance.., witness..] (n_instance + n_witness elements, canonical LE).
+ * r, s: the two blinding scalars, canonical LE, drawn by the caller with ark semantics
+ *       (`Fr::rand(rng)` twice) so the RNG stays on the Rust side.
+ * proof_out: A.x | A.y | B.x.c0 | B.x.c1 | B.y.c0 | B.y.c1 | C.x | C.y, canonical LE (8 |Fq| bytes) —
+ *       the coordinate order `parse_g1`/`parse_g2` hex-encode (zokrates_ark/src/lib.rs:150-218). */
+int32_t zkb_groth16_prove(zkb_ctx* ctx, uint64_t pk_handle, uint64_t r1cs_handle, const uint64_t* z,
+                          const uint64_t* r, const uint64_t* s, uint8_t* proof_out, size_t proof_cap);
+
+/* Same with the assignment already resident in HBM (set by zkb_r1cs_set_assignment): the
+ * kernel-only timing region of bench.py. */
+int32_t zkb_r1cs_set_assignment(zkb_ctx* ctx, uint64_t r1cs_handle, const uint64_t* z);
+int32_t zkb_groth16_prove_resident(zkb_ctx* ctx, uint64_t pk_handle, uint64_t r1cs_handle,
+                                   const uint64_t* r, const uint64_t* s, uint8_t* proof_out, size_t proof_cap);
+
+/* Multi-GPU: every rank computes the partial sums of its index slice (opaque blob, host memory,
+ * zkb_curve_sizes()[3] bytes); the host gathers the `world` blobs (torch.distributed all_gather over
+ * NCCL) and any rank finishes the proof. */
+int32_t zkb_groth16_prove_partial(zkb_ctx* ctx, uint64_t pk_handle, uint64_t r1cs_handle, const uint64_t* z,
+                                  uint8_t* partial_out, size_t partial_cap);
+int32_t zkb_groth16_finalize(zkb_ctx* ctx, uint64_t pk_handle, const uint8_t* partials, uint32_t world,
+                             const uint64_t* r, const uint64_t* s, uint8_t* proof_out, size_t proof_cap);
+
+/* ---- building blocks (micro-benchmarks and parity tests; BASELINE.json config 5) ---------------
+ * points: ark uncompressed affine encoding (x | y, canonical LE, infinity flag 0x40 in the last
+ * byte) as in proving.key; scalars canonical LE 32 bytes; out: one point in the same encoding.
+ * Replaces `VariableBaseMSM::multi_scalar_mul` (ark-ec 0.3.0). */
+int32_t zkb_msm_g1(zkb_ctx* ctx, const uint8_t* points, const uint64_t* scalars, uint64_t n, uint8_t* out);
+int32_t zkb_msm_g2(zkb_ctx* ctx, const uint8_t* points, const uint64_t* scalars, uint64_t n, uint8_t* out);
+/* In-place size-2^log_n transform of canonical LE Fr elements, natural order in and out.
+ * Replaces ark-poly `Radix2EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place`. */
+int32_t zkb_ntt(zkb_ctx* ctx, uint64_t* data, uint32_t log_n, int32_t inverse, int32_t coset);
+/* h = witness_map(r1cs, z): domain-size canonical LE coefficients (ark `R1CSToQAP::witness_map`). */
+int32_t zkb_witness_map(zkb_ctx* ctx, uint64_t r1cs_handle, const uint64_t* z, uint64_t* h_out, uint64_t h_cap_elems);
+/* Batched field arithmetic on canonical LE operands: field 0 = Fr, 1 = Fq; op 0 = mul, 1 = add,
+ * 2 = sub, 3 = inverse(a).  Replaces the `Field` ops of zokrates_field/src/lib.rs:407-503. */
+int32_t zkb_field_op(zkb_ctx* ctx, int32_t field, int32_t op, const uint64_t* a, const uint64_t* b, uint64_t* out,
+                     uint64_t n);
+
+/* ---- setup ("next" row: NonUniversalBackend::setup, zokrates_ark/src/groth16.rs:90-109) ---------
+ * Deterministic circuit-specific setup from an explicit trapdoor (alpha, beta, gamma, delta, tau and
+ * the discrete logs of the two generators w.r.t. the standard ones), all canonical LE Fr.  Writes an
+ * ark-format proving key (same bytes `serialize_unchecked` would produce for these parameters). */
+int32_t zkb_groth16_setup(zkb_ctx* ctx, uint64_t r1cs_handle, const uint64_t* trapdoor7, uint8_t* pk_out,
+                          size_t pk_cap, size_t* pk_len);
+/* bytes zkb_groth16_setup will write for this R1CS */
+int32_t zkb_groth16_setup_size(zkb_ctx* ctx, uint64_t r1cs_handle, size_t* pk_len);
+
+/* ---- measurement ------------------------------------------------------------------------------
+ * Per-stage device times (ms, CUDA events on the engine's stream) of the last prove/msm/ntt call.
+ * names: static strings, one per slot; returns the number of slots filled. */
+int32_t zkb_last_timings(zkb_ctx* ctx, double* ms_out, const char** names_out, int32_t cap);
+/* Kernels launched by this context so far (bench.py's gpu_launches). */
+uint64_t zkb_launch_count(zkb_ctx* ctx);
+/* Integer-pipe peak probes used as roofline denominators: kind 0 = dependent-free IMAD.WIDE.U32
+ * chain (returns 32x32+64 MAD/s), kind 1 = register-resident Montgomery multiplications in Fq
+ * (returns field-mul/s).  `iters` controls the duration. */
+int32_t zkb_peak_probe(zkb_ctx* ctx, int32_t kind, uint32_t iters, double* out_per_sec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKB_H */

@@ -1,0 +1,261 @@
+// C ABI of libzkb200.so (include/zkb.h).  No exception or CUDA type crosses this boundary.
+#include <memory>
+#include <string>
+#include <vector>
+#include "zkb.h"
+#include "engine_base.cuh"
+#include "probe.cuh"
+#if defined(ZKB_EMU)  // the host-emulation test build is a single translation unit
+#include "engine_bn254.cu"
+#include "engine_bls12_381.cu"
+#endif
+
+using namespace zkb;
+
+struct zkb_ctx {
+  int curve = 0;
+  int device = 0;
+  Stream st;
+  std::unique_ptr<EngineBase> eng;
+  uint64_t launches0 = 0;
+};
+
+static thread_local std::string g_err;
+
+template <class Fn>
+static int32_t guard(zkb_ctx* ctx, Fn fn) {
+  try {
+    if (!ctx || !ctx->eng) throw Error(ZKB_E_ARG, "null context");
+#if !defined(ZKB_EMU)
+    ZKB_CUDA(cudaSetDevice(ctx->device));
+#endif
+    fn();
+    return ZKB_OK;
+  } catch (const Error& e) {
+    g_err = e.what();
+#if !defined(ZKB_EMU)
+    cudaGetLastError();  // clear a sticky launch-configuration error
+#endif
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    g_err = "host allocation failed";
+    return ZKB_E_OOM;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return ZKB_E_INTERNAL;
+  } catch (...) {
+    g_err = "unknown error";
+    return ZKB_E_INTERNAL;
+  }
+}
+
+extern "C" {
+
+const char* zkb_last_error(void) { return g_err.c_str(); }
+uint32_t zkb_abi_version(void) { return 1; }
+
+int32_t zkb_device_count(void) {
+#if !defined(ZKB_EMU)
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    g_err = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e);
+    cudaGetLastError();
+    return -1;
+  }
+  return n;
+#else
+  return 1;
+#endif
+}
+
+int32_t zkb_ctx_create(int32_t curve, int32_t device, zkb_ctx** out) {
+  if (!out) { g_err = "out is null"; return ZKB_E_ARG; }
+  *out = nullptr;
+  try {
+    if (curve != ZKB_CURVE_BN128 && curve != ZKB_CURVE_BLS12_381) throw Error(ZKB_E_ARG, "unknown curve id");
+    std::unique_ptr<zkb_ctx> c(new zkb_ctx());
+    c->curve = curve;
+    c->device = device;
+#if !defined(ZKB_EMU)
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+      cudaGetLastError();
+      throw Error(ZKB_E_CUDA, std::string("no usable CUDA device (libzkb200 has no CPU fallback): ") +
+                                  (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    }
+    if (device < 0 || device >= n) throw Error(ZKB_E_ARG, "device index out of range");
+    ZKB_CUDA(cudaSetDevice(device));
+    ZKB_CUDA(cudaStreamCreateWithFlags(&c->st.s, cudaStreamNonBlocking));
+#endif
+    c->eng.reset(curve == ZKB_CURVE_BN128 ? make_engine_bn254(c->st) : make_engine_bls12_381(c->st));
+    c->launches0 = launch_counter();
+    *out = c.release();
+    return ZKB_OK;
+  } catch (const Error& e) {
+    g_err = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return ZKB_E_INTERNAL;
+  }
+}
+
+void zkb_ctx_destroy(zkb_ctx* ctx) {
+  if (!ctx) return;
+#if !defined(ZKB_EMU)
+  cudaSetDevice(ctx->device);
+  if (ctx->st.s) cudaStreamSynchronize(ctx->st.s);
+#endif
+  ctx->eng.reset();
+#if !defined(ZKB_EMU)
+  if (ctx->st.s) cudaStreamDestroy(ctx->st.s);
+#endif
+  delete ctx;
+}
+
+int32_t zkb_curve_sizes(int32_t curve, uint64_t out[4]) {
+  if (!out) { g_err = "out is null"; return ZKB_E_ARG; }
+  if (curve == ZKB_CURVE_BN128) {
+    out[0] = 32; out[1] = 32; out[2] = 256; out[3] = partial_bytes_bn254();
+  } else if (curve == ZKB_CURVE_BLS12_381) {
+    out[0] = 32; out[1] = 48; out[2] = 384; out[3] = partial_bytes_bls12_381();
+  } else {
+    g_err = "unknown curve id";
+    return ZKB_E_ARG;
+  }
+  return ZKB_OK;
+}
+
+int32_t zkb_pk_load(zkb_ctx* ctx, const uint8_t* pk, size_t len, uint32_t rank, uint32_t world, uint64_t* h) {
+  return guard(ctx, [&] {
+    if (!pk || !h) throw Error(ZKB_E_ARG, "null argument");
+    *h = ctx->eng->pk_load(pk, len, rank, world);
+  });
+}
+int32_t zkb_pk_info(zkb_ctx* ctx, uint64_t h, uint64_t out[4]) {
+  return guard(ctx, [&] { if (!out) throw Error(ZKB_E_ARG, "null"); ctx->eng->pk_info(h, out); });
+}
+int32_t zkb_pk_free(zkb_ctx* ctx, uint64_t h) { return guard(ctx, [&] { ctx->eng->pk_free(h); }); }
+
+int32_t zkb_r1cs_load(zkb_ctx* ctx, uint64_t N, uint64_t ni, uint64_t nw, const uint64_t* a_rowptr, const uint32_t* a_col,
+                      const uint64_t* a_val, const uint64_t* b_rowptr, const uint32_t* b_col, const uint64_t* b_val,
+                      const uint64_t* c_rowptr, const uint32_t* c_col, const uint64_t* c_val, uint64_t* h) {
+  return guard(ctx, [&] {
+    if (!a_rowptr || !b_rowptr || !c_rowptr || !h) throw Error(ZKB_E_ARG, "null argument");
+    const uint64_t* rp[3] = {a_rowptr, b_rowptr, c_rowptr};
+    const uint32_t* cl[3] = {a_col, b_col, c_col};
+    const uint64_t* vl[3] = {a_val, b_val, c_val};
+    *h = ctx->eng->r1cs_load(N, ni, nw, rp, cl, vl);
+  });
+}
+int32_t zkb_r1cs_free(zkb_ctx* ctx, uint64_t h) { return guard(ctx, [&] { ctx->eng->r1cs_free(h); }); }
+
+int32_t zkb_r1cs_set_assignment(zkb_ctx* ctx, uint64_t h, const uint64_t* z) {
+  return guard(ctx, [&] { if (!z) throw Error(ZKB_E_ARG, "null"); ctx->eng->set_assignment(h, z); });
+}
+
+static void check_proof_cap(zkb_ctx* ctx, size_t cap) {
+  uint64_t sz[4];
+  ctx->eng->sizes(sz);
+  if (cap < sz[2]) throw Error(ZKB_E_ARG, "proof_out too small");
+}
+
+static void prove_common(zkb_ctx* ctx, uint64_t pk, uint64_t r1cs, const uint64_t* z, const uint64_t* r, const uint64_t* s,
+                         uint8_t* proof_out, size_t cap) {
+  if (!r || !s || !proof_out) throw Error(ZKB_E_ARG, "null argument");
+  check_proof_cap(ctx, cap);
+  uint64_t sz[4];
+  ctx->eng->sizes(sz);
+  std::vector<uint8_t> partial(sz[3]);
+  ctx->eng->prove_partial(pk, r1cs, z, partial.data());
+  ctx->eng->finalize(pk, partial.data(), 1, r, s, proof_out);
+}
+
+int32_t zkb_groth16_prove(zkb_ctx* ctx, uint64_t pk, uint64_t r1cs, const uint64_t* z, const uint64_t* r, const uint64_t* s,
+                          uint8_t* proof_out, size_t cap) {
+  return guard(ctx, [&] {
+    if (!z) throw Error(ZKB_E_ARG, "null assignment");
+    prove_common(ctx, pk, r1cs, z, r, s, proof_out, cap);
+  });
+}
+int32_t zkb_groth16_prove_resident(zkb_ctx* ctx, uint64_t pk, uint64_t r1cs, const uint64_t* r, const uint64_t* s,
+                                   uint8_t* proof_out, size_t cap) {
+  return guard(ctx, [&] { prove_common(ctx, pk, r1cs, nullptr, r, s, proof_out, cap); });
+}
+int32_t zkb_groth16_prove_partial(zkb_ctx* ctx, uint64_t pk, uint64_t r1cs, const uint64_t* z, uint8_t* partial_out,
+                                  size_t cap) {
+  return guard(ctx, [&] {
+    uint64_t sz[4];
+    ctx->eng->sizes(sz);
+    if (!partial_out || cap < sz[3]) throw Error(ZKB_E_ARG, "partial_out too small");
+    ctx->eng->prove_partial(pk, r1cs, z, partial_out);
+  });
+}
+int32_t zkb_groth16_finalize(zkb_ctx* ctx, uint64_t pk, const uint8_t* partials, uint32_t world, const uint64_t* r,
+                             const uint64_t* s, uint8_t* proof_out, size_t cap) {
+  return guard(ctx, [&] {
+    if (!partials || !r || !s || !proof_out) throw Error(ZKB_E_ARG, "null argument");
+    check_proof_cap(ctx, cap);
+    ctx->eng->timings.clear();
+    ctx->eng->finalize(pk, partials, world, r, s, proof_out);
+  });
+}
+
+int32_t zkb_msm_g1(zkb_ctx* ctx, const uint8_t* points, const uint64_t* scalars, uint64_t n, uint8_t* out) {
+  return guard(ctx, [&] {
+    if (!out || (n && (!points || !scalars))) throw Error(ZKB_E_ARG, "null argument");
+    ctx->eng->msm(1, points, scalars, n, out);
+  });
+}
+int32_t zkb_msm_g2(zkb_ctx* ctx, const uint8_t* points, const uint64_t* scalars, uint64_t n, uint8_t* out) {
+  return guard(ctx, [&] {
+    if (!out || (n && (!points || !scalars))) throw Error(ZKB_E_ARG, "null argument");
+    ctx->eng->msm(2, points, scalars, n, out);
+  });
+}
+int32_t zkb_ntt(zkb_ctx* ctx, uint64_t* data, uint32_t log_n, int32_t inverse, int32_t coset) {
+  return guard(ctx, [&] { if (!data) throw Error(ZKB_E_ARG, "null"); ctx->eng->ntt(data, log_n, inverse, coset); });
+}
+int32_t zkb_witness_map(zkb_ctx* ctx, uint64_t r1cs, const uint64_t* z, uint64_t* h_out, uint64_t cap) {
+  return guard(ctx, [&] { if (!z || !h_out) throw Error(ZKB_E_ARG, "null"); ctx->eng->witness_map(r1cs, z, h_out, cap); });
+}
+int32_t zkb_field_op(zkb_ctx* ctx, int32_t field, int32_t op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n) {
+  return guard(ctx, [&] {
+    if (!a || !out) throw Error(ZKB_E_ARG, "null argument");
+    if (n) ctx->eng->field_op(field, op, a, b, out, n);
+  });
+}
+
+int32_t zkb_groth16_setup_size(zkb_ctx* ctx, uint64_t r1cs, size_t* len) {
+  return guard(ctx, [&] { if (!len) throw Error(ZKB_E_ARG, "null"); *len = ctx->eng->setup_size(r1cs); });
+}
+int32_t zkb_groth16_setup(zkb_ctx* ctx, uint64_t r1cs, const uint64_t* trapdoor7, uint8_t* pk_out, size_t cap, size_t* len) {
+  return guard(ctx, [&] {
+    if (!trapdoor7 || !pk_out || !len) throw Error(ZKB_E_ARG, "null argument");
+    ctx->eng->setup(r1cs, trapdoor7, pk_out, cap, len);
+  });
+}
+
+int32_t zkb_last_timings(zkb_ctx* ctx, double* ms_out, const char** names_out, int32_t cap) {
+  if (!ctx || !ctx->eng) return 0;
+  int32_t k = 0;
+  for (auto& e : ctx->eng->timings) {
+    if (k >= cap) break;
+    if (ms_out) ms_out[k] = e.second;
+    if (names_out) names_out[k] = e.first;
+    k++;
+  }
+  return k;
+}
+uint64_t zkb_launch_count(zkb_ctx* ctx) { return ctx ? launch_counter() - ctx->launches0 : 0; }
+
+int32_t zkb_peak_probe(zkb_ctx* ctx, int32_t kind, uint32_t iters, double* out) {
+  return guard(ctx, [&] {
+    if (!out) throw Error(ZKB_E_ARG, "null");
+    *out = peak_probe(ctx->st, kind, iters);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,824 @@
+// Per-curve proving engine: owns the resident proving key shards, R1CS matrices, NTT domain tables
+// and MSM workspaces of ONE GPU and sequences the kernels of the Groth16 prover.
+//
+// Follows ark-groth16 0.3.0 `create_proof_with_reduction` (external crate; call site
+// /root/reference/zokrates_ark/src/groth16.rs:44; restated in SURVEY.md App. B.1):
+//   h = witness_map(A z, B z, C z);  H = <h_query, h>;  L = <l_query, aux>;
+//   A = r d1 + a_0 + <a_query[1..], z[1..]> + alpha1;   B likewise in G1 and G2;
+//   C = s A + r B1 - r s d1 + L + H.
+// Everything from "z on the host" to "three affine points on the host" runs on the device.
+#pragma once
+#include <map>
+#include <memory>
+#include <vector>
+#include "msm.cuh"
+#include "ntt.cuh"
+#include "rt.cuh"
+#include "engine_base.cuh"
+
+namespace zkb {
+
+// kernel name tags (show up in ncu / nsys kernel names)
+struct k_fr_convert; struct k_spmv; struct k_ntt_dif; struct k_ntt_dit; struct k_ntt_scale; struct k_ntt_brev;
+struct k_ntt_table; struct k_qap_pointwise; struct k_msm_digits; struct k_msm_scatter; struct k_msm_accum1;
+struct k_msm_accum2; struct k_msm_tree; struct k_msm_horner; struct k_pk_convert; struct k_final_a; struct k_final_b;
+struct k_final_c; struct k_final_d; struct k_point_out; struct k_field_op; struct k_setup_scalars; struct k_fixed_base;
+struct k_to_affine; struct k_copy;
+
+// ---------------------------------------------------------------------------------------------
+// stage timer: CUDA events on the engine stream (no-op in the host emulation)
+struct StageTimer {
+#if !defined(ZKB_EMU)
+  struct Ev { const char* name; cudaEvent_t a, b; };
+  std::vector<Ev> evs;
+  Stream st;
+  explicit StageTimer(Stream s) : st(s) {}
+  void begin(const char* name) {
+    Ev e{name, nullptr, nullptr};
+    ZKB_CUDA(cudaEventCreate(&e.a));
+    ZKB_CUDA(cudaEventCreate(&e.b));
+    ZKB_CUDA(cudaEventRecord(e.a, st.s));
+    evs.push_back(e);
+  }
+  void end() { ZKB_CUDA(cudaEventRecord(evs.back().b, st.s)); }
+  void collect(std::vector<std::pair<const char*, double>>& out) {
+    out.clear();
+    for (auto& e : evs) {
+      ZKB_CUDA(cudaEventSynchronize(e.b));
+      float ms = 0;
+      ZKB_CUDA(cudaEventElapsedTime(&ms, e.a, e.b));
+      out.push_back({e.name, (double)ms});
+      cudaEventDestroy(e.a);
+      cudaEventDestroy(e.b);
+    }
+    evs.clear();
+  }
+  ~StageTimer() { for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); } }
+#else
+  explicit StageTimer(Stream) {}
+  void begin(const char*) {}
+  void end() {}
+  void collect(std::vector<std::pair<const char*, double>>& out) { out.clear(); }
+#endif
+};
+
+// exclusive scan of NB counters -> offsets[NB+1]
+#if !defined(ZKB_EMU)
+static __global__ void zkb_scan_kernel(const uint32_t* counts, uint32_t* offsets, uint32_t n) {
+  __shared__ uint32_t sums[1024];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t per = (n + 1023u) / 1024u;
+  const uint32_t lo = tid * per < n ? tid * per : n;
+  const uint32_t hi = lo + per < n ? lo + per : n;
+  uint32_t s = 0;
+  for (uint32_t i = lo; i < hi; i++) s += counts[i];
+  sums[tid] = s;
+  __syncthreads();
+  for (uint32_t off = 1; off < 1024; off <<= 1) {
+    uint32_t v = tid >= off ? sums[tid - off] : 0;
+    __syncthreads();
+    sums[tid] += v;
+    __syncthreads();
+  }
+  uint32_t base = tid ? sums[tid - 1] : 0;
+  for (uint32_t i = lo; i < hi; i++) {
+    offsets[i] = base;
+    base += counts[i];
+  }
+  if (tid == 1023) offsets[n] = sums[1023];
+}
+#endif
+inline void exclusive_scan(Stream st, const uint32_t* counts, uint32_t* offsets, uint32_t n) {
+#if !defined(ZKB_EMU)
+  launch_counter()++;
+  zkb_scan_kernel<<<1, 1024, 0, st.s>>>(counts, offsets, n);
+  ZKB_CUDA(cudaGetLastError());
+#else
+  uint32_t base = 0;
+  for (uint32_t i = 0; i < n; i++) { offsets[i] = base; base += counts[i]; }
+  offsets[n] = base;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+struct MsmPlan {
+  MsmShape sh{0, 0, 0, 0};
+  uint32_t nbuckets = 0;
+  uint32_t T1 = 32, T2 = 32;
+  uint32_t nt1 = 0;  // level-1 chunks
+  DevBuf<uint32_t> digits, counts, offsets, cursor, sorted;
+};
+
+inline uint32_t msm_pick_c(uint64_t n, int fr_bits) {
+  uint32_t best = 4;
+  double best_cost = 1e300;
+  for (uint32_t c = 4; c <= 16; c++) {
+    double W = (double)((fr_bits + 1 + c - 1) / c);
+    double cost = W * (10.0 * (double)n + 40.0 * (double)(1u << (c - 1)));
+    if (cost < best_cost) { best_cost = cost; best = c; }
+  }
+  return best;
+}
+
+// fixed-base window table: table[j * 256 + d] = d * 2^(8 j) * G, j < 32 (setup.cuh)
+template <class F>
+struct FixedBase {
+  DevBuf<Affine<F>> table;
+  DevBuf<XYZZ<F>> bases;
+};
+
+template <class FrP, class FqP>
+struct CurveT {
+  typedef Fp<FrP> Fr;
+  typedef Fp<FqP> Fq;
+  typedef Fp2<FqP> Fq2;
+  typedef Affine<Fq> G1A;
+  typedef Affine<Fq2> G2A;
+  typedef XYZZ<Fq> G1X;
+  typedef XYZZ<Fq2> G2X;
+  static constexpr int FR_BITS = FrP::BITS;
+  static constexpr int FQ_BYTES = FqP::N * 4;
+};
+
+template <class C>
+class Engine : public EngineBase {
+ public:
+  typedef typename C::Fr Fr;
+  typedef typename C::Fq Fq;
+  typedef typename C::Fq2 Fq2;
+  typedef typename C::G1A G1A;
+  typedef typename C::G2A G2A;
+  typedef typename C::G1X G1X;
+  typedef typename C::G2X G2X;
+  static constexpr size_t FRB = 32, FQB = C::FQ_BYTES, G1B = 2 * FQB, G2B = 4 * FQB;
+  static_assert(sizeof(Fr) == 32 && sizeof(G1A) == G1B && sizeof(G2A) == G2B, "layout");
+
+  struct Partial {  // per-rank partial sums, in this order
+    G1X h, l, a, b1;
+    G2X b2;
+  };
+
+  explicit Engine(Stream st) : st_(st) {}
+
+  void sizes(uint64_t out[4]) override {
+    out[0] = FRB; out[1] = FQB; out[2] = 8 * FQB; out[3] = sizeof(Partial);
+  }
+
+  // ------------------------------------------------------------------------------ domains
+  struct DomainT {
+    uint32_t log_n = 0;
+    DevBuf<Fr> tw_fwd, tw_inv, cos_fwd, cos_inv;  // w^k, w^-k (k < n/2);  g^k / n, g^-k / n (k < n)
+    Fr zinv;                                      // 1 / (g^n - 1)
+    Fr ninv;
+  };
+  std::map<uint32_t, std::unique_ptr<DomainT>> domains_;
+
+  static Fr fr_gen() { Fr g; for (int i = 0; i < Fr::N; i++) g.v[i] = Fr::Params::gen(i); return g; }
+  static Fr fr_root() { Fr g; for (int i = 0; i < Fr::N; i++) g.v[i] = Fr::Params::root(i); return g; }
+  static Fr fr_omega(uint32_t log_n) {
+    Fr w = fr_root();
+    for (uint32_t i = log_n; i < (uint32_t)Fr::Params::TWO_ADICITY; i++) w = Fr::sqr(w);
+    return w;
+  }
+
+  DomainT& domain(uint32_t log_n) {
+    auto it = domains_.find(log_n);
+    if (it != domains_.end()) return *it->second;
+    if (log_n > (uint32_t)Fr::Params::TWO_ADICITY || log_n > 28) throw Error(ZKB_E_ARG, "domain too large");
+    std::unique_ptr<DomainT> d(new DomainT());
+    d->log_n = log_n;
+    const uint32_t n = 1u << log_n;
+    Fr w = fr_omega(log_n), wi = Fr::inv(w), g = fr_gen(), gi = Fr::inv(g);
+    Fr nf = Fr::to_mont(fr_from_u64(n));
+    d->ninv = Fr::inv(nf);
+    d->zinv = Fr::inv(Fr::sub(Fr::pow_u64(g, n), Fr::one()));
+    d->tw_fwd.alloc(n / 2 + 1); d->tw_inv.alloc(n / 2 + 1); d->cos_fwd.alloc(n); d->cos_inv.alloc(n);
+    Fr one = Fr::one(), ninv = d->ninv;
+    Fr* p0 = d->tw_fwd.p; Fr* p1 = d->tw_inv.p; Fr* p2 = d->cos_fwd.p; Fr* p3 = d->cos_inv.p;
+    launch<k_ntt_table>(st_, n / 2, ZKB_LAMBDA(size_t t) { ntt_powers_body<Fr>(w, one, p0, n / 2, (uint32_t)t); });
+    launch<k_ntt_table>(st_, n / 2, ZKB_LAMBDA(size_t t) { ntt_powers_body<Fr>(wi, one, p1, n / 2, (uint32_t)t); });
+    launch<k_ntt_table>(st_, n, ZKB_LAMBDA(size_t t) { ntt_powers_body<Fr>(g, ninv, p2, n, (uint32_t)t); });
+    launch<k_ntt_table>(st_, n, ZKB_LAMBDA(size_t t) { ntt_powers_body<Fr>(gi, ninv, p3, n, (uint32_t)t); });
+    DomainT& ref = *d;
+    domains_[log_n] = std::move(d);
+    return ref;
+  }
+
+  static Fr fr_from_u64(uint64_t v) {
+    Fr r = Fr::zero();
+    r.v[0] = (uint32_t)v;
+    r.v[1] = (uint32_t)(v >> 32);
+    return r;
+  }
+
+  // natural -> bit-reversed
+  void ntt_dif(Fr* x, const Fr* tw, uint32_t log_n) {
+    uint32_t h = (1u << log_n) >> 1, rem = log_n;
+    const size_t n = (size_t)1 << log_n;
+    while (rem > 0) {
+      uint32_t K = rem >= 3 ? 3 : rem;
+      uint32_t h0 = h;
+      if (K == 3) launch<k_ntt_dif>(st_, n >> 3, ZKB_LAMBDA(size_t t) { ntt_dif_body<Fr, 3>(x, tw, log_n, h0, (uint32_t)t); });
+      else if (K == 2) launch<k_ntt_dif>(st_, n >> 2, ZKB_LAMBDA(size_t t) { ntt_dif_body<Fr, 2>(x, tw, log_n, h0, (uint32_t)t); });
+      else launch<k_ntt_dif>(st_, n >> 1, ZKB_LAMBDA(size_t t) { ntt_dif_body<Fr, 1>(x, tw, log_n, h0, (uint32_t)t); });
+      h >>= K;
+      rem -= K;
+    }
+  }
+  // bit-reversed -> natural
+  void ntt_dit(Fr* x, const Fr* tw, uint32_t log_n) {
+    uint32_t h = 1, rem = log_n;
+    const size_t n = (size_t)1 << log_n;
+    while (rem > 0) {
+      uint32_t K = rem >= 3 ? 3 : rem;
+      uint32_t h0 = h;
+      if (K == 3) launch<k_ntt_dit>(st_, n >> 3, ZKB_LAMBDA(size_t t) { ntt_dit_body<Fr, 3>(x, tw, log_n, h0, (uint32_t)t); });
+      else if (K == 2) launch<k_ntt_dit>(st_, n >> 2, ZKB_LAMBDA(size_t t) { ntt_dit_body<Fr, 2>(x, tw, log_n, h0, (uint32_t)t); });
+      else launch<k_ntt_dit>(st_, n >> 1, ZKB_LAMBDA(size_t t) { ntt_dit_body<Fr, 1>(x, tw, log_n, h0, (uint32_t)t); });
+      h <<= K;
+      rem -= K;
+    }
+  }
+
+  void convert(const Fr* in, Fr* out, int dir, size_t n) {
+    launch<k_fr_convert>(st_, n, ZKB_LAMBDA(size_t t) { fr_convert_body<Fr>(in, out, dir, n, t); });
+  }
+
+  // zkb_ntt: natural order in/out, canonical LE on the host
+  void ntt(uint64_t* data, uint32_t log_n, int inverse, int coset) override {
+    StageTimer tm(st_);
+    DomainT& d = domain(log_n);
+    const size_t n = (size_t)1 << log_n;
+    scratch_a_.ensure(n);
+    scratch_b_.ensure(n);
+    Fr* x = scratch_a_.p;
+    Fr* y = scratch_b_.p;
+    h2d(st_, x, data, n * FRB);
+    convert(x, x, 0, n);
+    tm.begin("ntt");
+    if (!inverse) {
+      if (coset) {  // x[k] *= g^k  (table holds g^k / n: undo the 1/n)
+        const Fr* tab = d.cos_fwd.p;
+        Fr nf = Fr::to_mont(fr_from_u64(n));
+        launch<k_ntt_scale>(st_, n, ZKB_LAMBDA(size_t t) { x[t] = Fr::mul(Fr::mul(x[t], tab[t]), nf); });
+      }
+      ntt_dif(x, d.tw_fwd.p, log_n);
+      const Fr* nul = nullptr;
+      launch<k_ntt_brev>(st_, n, ZKB_LAMBDA(size_t t) { ntt_brev_copy_body<Fr>(x, y, nul, log_n, 1, (uint32_t)t); });
+    } else {
+      ntt_dif(x, d.tw_inv.p, log_n);
+      if (coset) {
+        const Fr* tab = d.cos_inv.p;
+        launch<k_ntt_brev>(st_, n, ZKB_LAMBDA(size_t t) { ntt_brev_copy_body<Fr>(x, y, tab, log_n, 1, (uint32_t)t); });
+      } else {
+        Fr ninv = d.ninv;
+        launch<k_ntt_brev>(st_, n, ZKB_LAMBDA(size_t t) {
+          uint32_t j = bitrev32((uint32_t)t, log_n);
+          y[j] = Fr::from_mont(Fr::mul(x[t], ninv));
+        });
+      }
+    }
+    tm.end();
+    d2h(st_, data, y, n * FRB);
+    stream_sync(st_);
+    tm.collect(timings);
+  }
+
+  // ------------------------------------------------------------------------------ R1CS
+  struct R1cs {
+    uint64_t N = 0, ni = 0, nw = 0, m = 0;
+    uint32_t log_n = 0;
+    DevBuf<uint32_t> rowptr[3], col[3];
+    DevBuf<Fr> val[3];
+    DevBuf<Fr> z_canon, z_mont, a, b, c, h;
+    bool has_z = false;
+    // host copies kept for setup (CSC transposition) — small relative to the device data
+    std::vector<uint32_t> h_rowptr[3], h_col[3];
+  };
+  std::map<uint64_t, std::unique_ptr<R1cs>> r1cs_;
+  uint64_t next_handle_ = 1;
+
+  R1cs& get_r1cs(uint64_t h) {
+    auto it = r1cs_.find(h);
+    if (it == r1cs_.end()) throw Error(ZKB_E_ARG, "unknown r1cs handle");
+    return *it->second;
+  }
+
+  uint64_t r1cs_load(uint64_t N, uint64_t ni, uint64_t nw, const uint64_t* const rowptr[3], const uint32_t* const col[3],
+                     const uint64_t* const val[3]) override {
+    if (ni < 1) throw Error(ZKB_E_ARG, "n_instance must count the constant one");
+    std::unique_ptr<R1cs> r(new R1cs());
+    r->N = N; r->ni = ni; r->nw = nw; r->m = ni + nw;
+    uint64_t dom = N + ni, n = 1;
+    uint32_t lg = 0;
+    while (n < dom) { n <<= 1; lg++; }
+    if (lg > 28 || r->m >= (1ull << 31)) throw Error(ZKB_E_ARG, "circuit too large");
+    r->log_n = lg;
+    for (int k = 0; k < 3; k++) {
+      uint64_t nnz = rowptr[k][N];
+      if (nnz >= (1ull << 32)) throw Error(ZKB_E_ARG, "too many non-zeros");
+      std::vector<uint32_t>& rp = r->h_rowptr[k];
+      rp.resize(N + 1);
+      for (uint64_t i = 0; i <= N; i++) {
+        if (rowptr[k][i] > nnz || (i && rowptr[k][i] < rowptr[k][i - 1])) throw Error(ZKB_E_ARG, "bad rowptr");
+        rp[i] = (uint32_t)rowptr[k][i];
+      }
+      r->h_col[k].assign(col[k], col[k] + nnz);
+      for (uint64_t i = 0; i < nnz; i++)
+        if (col[k][i] >= r->m) throw Error(ZKB_E_ARG, "column index out of range");
+      r->rowptr[k].alloc(N + 1);
+      r->col[k].alloc(nnz);
+      r->val[k].alloc(nnz);
+      h2d(st_, r->rowptr[k].p, rp.data(), (N + 1) * 4);
+      h2d(st_, r->col[k].p, col[k], nnz * 4);
+      h2d(st_, r->val[k].p, val[k], nnz * FRB);
+      convert(r->val[k].p, r->val[k].p, 0, nnz);
+    }
+    r->z_canon.alloc(r->m); r->z_mont.alloc(r->m);
+    r->a.alloc(n); r->b.alloc(n); r->c.alloc(n); r->h.alloc(n);
+    domain(lg);
+    stream_sync(st_);
+    uint64_t h = next_handle_++;
+    r1cs_[h] = std::move(r);
+    return h;
+  }
+  void r1cs_free(uint64_t h) override { r1cs_.erase(h); }
+
+  void set_assignment(uint64_t h, const uint64_t* z) override {
+    R1cs& r = get_r1cs(h);
+    h2d(st_, r.z_canon.p, z, r.m * FRB);
+    stream_sync(st_);
+    r.has_z = true;
+  }
+
+  // h (canonical, natural order) = witness_map(z)   [device-resident]
+  void witness_map_dev(R1cs& r, StageTimer& tm) {
+    DomainT& d = domain(r.log_n);
+    const uint32_t lg = r.log_n;
+    const size_t n = (size_t)1 << lg;
+    tm.begin("witness_map");
+    convert(r.z_canon.p, r.z_mont.p, 0, r.m);
+    Fr* vec[3] = {r.a.p, r.b.p, r.c.p};
+    const Fr* zm = r.z_mont.p;
+    for (int k = 0; k < 3; k++) {
+      Fr* out = vec[k];
+      const uint32_t* rp = r.rowptr[k].p;
+      const uint32_t* cl = r.col[k].p;
+      const Fr* vl = r.val[k].p;
+      const uint32_t N = (uint32_t)r.N;
+      dev_zero(st_, out + r.N, (n - r.N) * FRB);
+      launch<k_spmv>(st_, r.N, ZKB_LAMBDA(size_t t) { spmv_body<Fr>(rp, cl, vl, zm, out, N, (uint32_t)t); });
+    }
+    d2d(st_, r.a.p + r.N, r.z_mont.p, r.ni * FRB);  // a[N + j] = z[j] for the instance variables
+    const Fr* t1 = d.cos_fwd.p;
+    for (int k = 0; k < 3; k++) {
+      Fr* x = vec[k];
+      ntt_dif(x, d.tw_inv.p, lg);
+      launch<k_ntt_scale>(st_, n, ZKB_LAMBDA(size_t t) { ntt_scale_brev_body<Fr>(x, t1, lg, (uint32_t)t); });
+      ntt_dit(x, d.tw_fwd.p, lg);
+    }
+    Fr* pa = r.a.p; const Fr* pb = r.b.p; const Fr* pc = r.c.p;
+    Fr zinv = d.zinv;
+    launch<k_qap_pointwise>(st_, n, ZKB_LAMBDA(size_t t) { qap_pointwise_body<Fr>(pa, pb, pc, zinv, (uint32_t)n, (uint32_t)t); });
+    ntt_dif(pa, d.tw_inv.p, lg);
+    Fr* ph = r.h.p;
+    const Fr* t2 = d.cos_inv.p;
+    launch<k_ntt_brev>(st_, n, ZKB_LAMBDA(size_t t) { ntt_brev_copy_body<Fr>(pa, ph, t2, lg, 1, (uint32_t)t); });
+    tm.end();
+  }
+
+  void witness_map(uint64_t h, const uint64_t* z, uint64_t* h_out, uint64_t cap) override {
+    R1cs& r = get_r1cs(h);
+    const size_t n = (size_t)1 << r.log_n;
+    if (cap < n) throw Error(ZKB_E_ARG, "h_out too small");
+    StageTimer tm(st_);
+    h2d(st_, r.z_canon.p, z, r.m * FRB);
+    witness_map_dev(r, tm);
+    d2h(st_, h_out, r.h.p, n * FRB);
+    stream_sync(st_);
+    tm.collect(timings);
+  }
+
+  // ------------------------------------------------------------------------------ MSM
+  DevBuf<uint8_t> ws_buckets_, ws_val_[2], ws_tree_[4], ws_result_;
+  DevBuf<uint32_t> ws_key_[2];
+
+  void plan_build(MsmPlan& pl, const Fr* scalars, uint64_t n) {
+    pl.sh.n = (uint32_t)n;
+    if (n == 0) return;
+    uint32_t c = msm_pick_c(n, C::FR_BITS);
+    pl.sh.c = c;
+    pl.sh.W = (C::FR_BITS + 1 + c - 1) / c;
+    pl.sh.B = 1u << (c - 1);
+    pl.nbuckets = pl.sh.W * pl.sh.B;
+    uint64_t total = n * pl.sh.W;
+    if (total >= (1ull << 32)) throw Error(ZKB_E_ARG, "msm too large");
+    // chunk size: aim for several waves of resident threads, at least 8 entries per chunk
+    uint64_t target = 600000;
+    uint64_t T = (total + target - 1) / target;
+    if (T < 8) T = 8;
+    if (T > 64) T = 64;
+    T = (T + 1) & ~1ull;
+    pl.T1 = (uint32_t)T;
+    pl.T2 = 32;
+    pl.nt1 = (uint32_t)((total + pl.T1 - 1) / pl.T1);
+    pl.digits.ensure(total); pl.sorted.ensure(total);
+    pl.counts.ensure(pl.nbuckets); pl.cursor.ensure(pl.nbuckets); pl.offsets.ensure(pl.nbuckets + 1);
+    dev_zero(st_, pl.counts.p, (size_t)pl.nbuckets * 4);
+    dev_zero(st_, pl.cursor.p, (size_t)pl.nbuckets * 4);
+    MsmShape sh = pl.sh;
+    const uint32_t* sc = (const uint32_t*)scalars;
+    uint32_t* dg = pl.digits.p; uint32_t* cn = pl.counts.p; uint32_t* of = pl.offsets.p; uint32_t* cu = pl.cursor.p;
+    uint32_t* so = pl.sorted.p;
+    launch<k_msm_digits>(st_, n, ZKB_LAMBDA(size_t t) { msm_digits_body(sh, sc, dg, cn, (uint32_t)t); });
+    exclusive_scan(st_, cn, of, pl.nbuckets);
+    launch<k_msm_scatter>(st_, total, ZKB_LAMBDA(size_t t) { msm_scatter_body(sh, dg, of, cu, so, t); });
+  }
+
+  template <class F>
+  void msm_exec(const MsmPlan& pl, const Affine<F>* pts, XYZZ<F>* result) {
+    typedef XYZZ<F> X;
+    if (pl.sh.n == 0) { dev_zero(st_, result, sizeof(X)); return; }
+    const uint32_t NB = pl.nbuckets, W = pl.sh.W, B = pl.sh.B, c = pl.sh.c;
+    ws_buckets_.ensure((size_t)NB * sizeof(X));
+    X* buckets = (X*)ws_buckets_.p;
+    dev_zero(st_, buckets, (size_t)NB * sizeof(X));
+    const uint32_t nt1 = pl.nt1, T1 = pl.T1, T2 = pl.T2;
+    for (int k = 0; k < 2; k++) { ws_key_[k].ensure(2 * (size_t)nt1 + 2); ws_val_[k].ensure((2 * (size_t)nt1 + 2) * sizeof(X)); }
+    const uint32_t* of = pl.offsets.p; const uint32_t* so = pl.sorted.p;
+    uint32_t* k0 = ws_key_[0].p; X* v0 = (X*)ws_val_[0].p;
+    launch<k_msm_accum1>(st_, nt1, ZKB_LAMBDA(size_t t) { msm_accum1_body<F>(NB, T1, of, so, pts, buckets, k0, v0, nt1, (uint32_t)t); });
+    uint32_t L = 2 * nt1;
+    int cur = 0;
+    while (true) {
+      uint32_t nt = L / T2 + 1;
+      const uint32_t* ik = ws_key_[cur].p; const X* iv = (const X*)ws_val_[cur].p;
+      uint32_t* ok = ws_key_[cur ^ 1].p; X* ov = (X*)ws_val_[cur ^ 1].p;
+      uint32_t Lc = L;
+      launch<k_msm_accum2>(st_, nt, ZKB_LAMBDA(size_t t) { msm_accum2_body<F>(Lc, T2, ik, iv, buckets, ok, ov, nt, (uint32_t)t); });
+      if (nt == 1) break;
+      L = 2 * nt;
+      cur ^= 1;
+    }
+    // bucket tree (fan-in 8) then Horner over the windows
+    const uint32_t lr = 3;
+    size_t first = (size_t)W * ((B + 7) / 8);
+    for (int k = 0; k < 4; k++) ws_tree_[k].ensure(first * sizeof(X));
+    const X* inA = buckets; const X* inWt = nullptr;
+    uint32_t cnt = B, lvl = 0;
+    int pp = 0;
+    while (cnt > 1) {
+      uint32_t cnt_out = (cnt + 7) / 8;
+      X* oA = (X*)ws_tree_[pp].p; X* oW = (X*)ws_tree_[pp + 1].p;
+      const X* iA = inA; const X* iW = inWt;
+      uint32_t ci = cnt, lv = lvl;
+      launch<k_msm_tree>(st_, (size_t)W * cnt_out, ZKB_LAMBDA(size_t t) { msm_tree_body<F>(W, ci, lr, lv, iA, iW, oA, oW, (uint32_t)t); });
+      inA = oA; inWt = oW; cnt = cnt_out; lvl++;
+      pp ^= 2;
+    }
+    const X* fA = inA; const X* fW = inWt;
+    launch<k_msm_horner, 1>(st_, 1, ZKB_LAMBDA(size_t) { msm_horner_body<F>(W, c, fA, fW, result); });
+  }
+
+  // ------------------------------------------------------------------------------ proving key
+  struct Pk {
+    uint64_t ni = 0, m = 0, hl = 0, ll = 0;
+    uint32_t rank = 0, world = 1;
+    uint64_t lo = 0, hi = 0, hlo = 0, hhi = 0;  // assignment / h index slices of this rank
+    DevBuf<G1A> a, b1, l, h;                    // a_query[1+lo..1+hi), b_g1 likewise, l_ext[lo..hi), h_query[hlo..hhi)
+    DevBuf<G2A> b2;
+    DevBuf<G1A> fixed1;                          // alpha1, beta1, delta1, a_query[0], b_g1_query[0]
+    DevBuf<G2A> fixed2;                          // beta2, delta2, b_g2_query[0]
+  };
+  std::map<uint64_t, std::unique_ptr<Pk>> pks_;
+  Pk& get_pk(uint64_t h) {
+    auto it = pks_.find(h);
+    if (it == pks_.end()) throw Error(ZKB_E_ARG, "unknown pk handle");
+    return *it->second;
+  }
+
+  template <class F>
+  void pk_convert(Affine<F>* pts, size_t count) {
+    launch<k_pk_convert>(st_, count, ZKB_LAMBDA(size_t t) {
+      Affine<F> p = pts[t];
+      uint32_t* raw = (uint32_t*)&p;
+      const int last = sizeof(Affine<F>) / 4 - 1;
+      bool inf = (raw[last] >> 30) & 1u;  // flag bit 6 of the last byte (ark SWFlags::infinity)
+      raw[last] &= 0x3FFFFFFFu;
+      if (inf) {
+        p = Affine<F>::inf();
+      } else {
+        p.x = F::to_mont(p.x);
+        p.y = F::to_mont(p.y);
+      }
+      pts[t] = p;
+    });
+  }
+
+  uint64_t pk_load(const uint8_t* pk, size_t len, uint32_t rank, uint32_t world) override {
+    if (world == 0 || rank >= world) throw Error(ZKB_E_ARG, "bad rank/world");
+    size_t off = 0;
+    auto need = [&](size_t k) { if (off + k > len) throw Error(ZKB_E_FORMAT, "proving key truncated"); };
+    auto take = [&](size_t k) { need(k); const uint8_t* p = pk + off; off += k; return p; };
+    auto take_len = [&]() { need(8); uint64_t v; memcpy(&v, pk + off, 8); off += 8; return v; };
+    const uint8_t* alpha1 = take(G1B);
+    const uint8_t* beta2 = take(G2B);
+    take(G2B);  // gamma_g2 (verifier only)
+    const uint8_t* delta2 = take(G2B);
+    uint64_t ni = take_len();
+    if (ni > (len - off) / G1B) throw Error(ZKB_E_FORMAT, "gamma_abc length");
+    take(ni * G1B);
+    const uint8_t* beta1 = take(G1B);
+    const uint8_t* delta1 = take(G1B);
+    uint64_t m = take_len();
+    if (m > (len - off) / G1B) throw Error(ZKB_E_FORMAT, "a_query length");
+    const uint8_t* aq = take(m * G1B);
+    uint64_t m1 = take_len();
+    if (m1 != m) throw Error(ZKB_E_FORMAT, "b_g1_query length differs from a_query");
+    const uint8_t* b1q = take(m * G1B);
+    uint64_t m2 = take_len();
+    if (m2 != m) throw Error(ZKB_E_FORMAT, "b_g2_query length differs from a_query");
+    const uint8_t* b2q = take(m * G2B);
+    uint64_t hl = take_len();
+    if (hl > (len - off) / G1B) throw Error(ZKB_E_FORMAT, "h_query length");
+    const uint8_t* hq = take(hl * G1B);
+    uint64_t ll = take_len();
+    if (ll > (len - off) / G1B) throw Error(ZKB_E_FORMAT, "l_query length");
+    const uint8_t* lq = take(ll * G1B);
+    if (off != len) throw Error(ZKB_E_FORMAT, "trailing bytes after proving key");
+    if (ni < 1 || m < ni || ll != m - ni) throw Error(ZKB_E_FORMAT, "inconsistent query lengths");
+
+    std::unique_ptr<Pk> p(new Pk());
+    p->ni = ni; p->m = m; p->hl = hl; p->ll = ll; p->rank = rank; p->world = world;
+    const uint64_t na = m - 1;  // pairs with assignment = z[1..]
+    p->lo = na * rank / world; p->hi = na * (rank + 1) / world;
+    p->hlo = hl * rank / world; p->hhi = hl * (rank + 1) / world;
+    const uint64_t cnt = p->hi - p->lo, hcnt = p->hhi - p->hlo;
+    p->a.alloc(cnt); p->b1.alloc(cnt); p->l.alloc(cnt); p->b2.alloc(cnt); p->h.alloc(hcnt);
+    h2d(st_, p->a.p, aq + (1 + p->lo) * G1B, cnt * G1B);
+    h2d(st_, p->b1.p, b1q + (1 + p->lo) * G1B, cnt * G1B);
+    h2d(st_, p->b2.p, b2q + (1 + p->lo) * G2B, cnt * G2B);
+    h2d(st_, p->h.p, hq + p->hlo * G1B, hcnt * G1B);
+    // l_ext[j] = infinity for j < ni - 1, else l_query[j - (ni - 1)]   (aux = assignment[ni-1..])
+    {
+      const uint64_t shift = ni - 1;
+      dev_zero(st_, p->l.p, cnt * G1B);
+      uint64_t j0 = p->lo > shift ? p->lo : shift;  // first assignment index with a real l point
+      if (j0 < p->hi) h2d(st_, p->l.p + (j0 - p->lo), lq + (j0 - shift) * G1B, (p->hi - j0) * G1B);
+    }
+    p->fixed1.alloc(5); p->fixed2.alloc(3);
+    std::vector<uint8_t> inf1(G1B, 0), inf2(G2B, 0);
+    inf1[G1B - 1] = 0x40; inf2[G2B - 1] = 0x40;
+    h2d(st_, p->fixed1.p + 0, alpha1, G1B);
+    h2d(st_, p->fixed1.p + 1, beta1, G1B);
+    h2d(st_, p->fixed1.p + 2, delta1, G1B);
+    h2d(st_, p->fixed1.p + 3, m ? aq : inf1.data(), G1B);
+    h2d(st_, p->fixed1.p + 4, m ? b1q : inf1.data(), G1B);
+    h2d(st_, p->fixed2.p + 0, beta2, G2B);
+    h2d(st_, p->fixed2.p + 1, delta2, G2B);
+    h2d(st_, p->fixed2.p + 2, m ? b2q : inf2.data(), G2B);
+    pk_convert<Fq>(p->a.p, cnt); pk_convert<Fq>(p->b1.p, cnt); pk_convert<Fq>(p->h.p, hcnt);
+    pk_convert<Fq2>(p->b2.p, cnt); pk_convert<Fq>(p->fixed1.p, 5); pk_convert<Fq2>(p->fixed2.p, 3);
+    {  // l_ext: only the uploaded part carries raw bytes; zero-filled prefix is already "infinity"
+      const uint64_t shift = ni - 1;
+      uint64_t j0 = p->lo > shift ? p->lo : shift;
+      if (j0 < p->hi) pk_convert<Fq>(p->l.p + (j0 - p->lo), p->hi - j0);
+    }
+    stream_sync(st_);
+    uint64_t h = next_handle_++;
+    pks_[h] = std::move(p);
+    return h;
+  }
+  void pk_info(uint64_t h, uint64_t out[4]) override {
+    Pk& p = get_pk(h);
+    out[0] = p.ni; out[1] = p.m; out[2] = p.hl; out[3] = p.ll;
+  }
+  void pk_free(uint64_t h) override { pks_.erase(h); }
+
+  // ------------------------------------------------------------------------------ prove
+  MsmPlan plan_z_, plan_h_;
+  DevBuf<Partial> d_partial_;
+  DevBuf<Fr> scratch_a_, scratch_b_;
+
+  void prove_partial(uint64_t pkh, uint64_t rh, const uint64_t* z, uint8_t* partial_out) override {
+    Pk& pk = get_pk(pkh);
+    R1cs& r = get_r1cs(rh);
+    const size_t n = (size_t)1 << r.log_n;
+    if (pk.m != r.m || pk.ni != r.ni) throw Error(ZKB_E_ARG, "proving key does not match the R1CS (variable counts)");
+    if (pk.hl + 1 != n && !(n == 1 && pk.hl == 0)) throw Error(ZKB_E_ARG, "proving key does not match the R1CS (domain size)");
+    StageTimer tm(st_);
+    if (z) {
+      tm.begin("h2d_z");
+      h2d(st_, r.z_canon.p, z, r.m * FRB);
+      tm.end();
+      r.has_z = true;
+    } else if (!r.has_z) {
+      throw Error(ZKB_E_ARG, "no resident assignment");
+    }
+    witness_map_dev(r, tm);
+    d_partial_.ensure(1);
+    Partial* out = d_partial_.p;
+    tm.begin("msm_plan_h");
+    plan_build(plan_h_, r.h.p + pk.hlo, pk.hhi - pk.hlo);
+    tm.end();
+    tm.begin("msm_h");
+    msm_exec<Fq>(plan_h_, pk.h.p, &out->h);
+    tm.end();
+    tm.begin("msm_plan_z");
+    plan_build(plan_z_, r.z_canon.p + 1 + pk.lo, pk.hi - pk.lo);
+    tm.end();
+    tm.begin("msm_l");
+    msm_exec<Fq>(plan_z_, pk.l.p, &out->l);
+    tm.end();
+    tm.begin("msm_a");
+    msm_exec<Fq>(plan_z_, pk.a.p, &out->a);
+    tm.end();
+    tm.begin("msm_b1");
+    msm_exec<Fq>(plan_z_, pk.b1.p, &out->b1);
+    tm.end();
+    tm.begin("msm_b2");
+    msm_exec<Fq2>(plan_z_, pk.b2.p, &out->b2);
+    tm.end();
+    d2h(st_, partial_out, out, sizeof(Partial));
+    stream_sync(st_);
+    tm.collect(timings);
+  }
+
+  struct FinalWs {
+    G1X t_rd, t_sd, t_rsd, ga, gb1, u1, u2, sum_h, sum_l, sum_a, sum_b1;
+    G2X t_sd2, gb2, sum_b2;
+  };
+  DevBuf<FinalWs> d_final_;
+  DevBuf<Partial> d_parts_;
+  DevBuf<uint32_t> d_rs_;
+  DevBuf<uint32_t> d_proof_;
+
+  void finalize(uint64_t pkh, const uint8_t* partials, uint32_t world, const uint64_t* r, const uint64_t* s,
+                uint8_t* proof_out) override {
+    Pk& pk = get_pk(pkh);
+    if (world == 0) throw Error(ZKB_E_ARG, "world");
+    StageTimer tm(st_);
+    d_parts_.ensure(world); d_final_.ensure(1); d_rs_.ensure(24); d_proof_.ensure(8 * FQB / 4);
+    h2d(st_, d_parts_.p, partials, world * sizeof(Partial));
+    h2d(st_, d_rs_.p, r, 32);
+    h2d(st_, d_rs_.p + 8, s, 32);
+    const Partial* parts = d_parts_.p;
+    FinalWs* ws = d_final_.p;
+    uint32_t* rs = d_rs_.p;
+    const G1A* f1 = pk.fixed1.p;
+    const G2A* f2 = pk.fixed2.p;
+    uint32_t* proof = d_proof_.p;
+    tm.begin("final_combine");
+    // phase A: independent scalar multiplications and the cross-rank sums, one thread-block each
+    launch<k_final_a, 1>(st_, 9, ZKB_LAMBDA(size_t role) {
+      const uint32_t* rr = rs;
+      const uint32_t* ss = rs + 8;
+      switch ((int)role) {
+        case 0: ws->t_rd = G1X::mul_affine(f1[2], rr, 8); break;
+        case 1: ws->t_sd = G1X::mul_affine(f1[2], ss, 8); break;
+        case 2: {
+          Fr a, b;
+          for (int i = 0; i < 8; i++) { a.v[i] = rr[i]; b.v[i] = ss[i]; }
+          Fr p = Fr::mul(Fr::to_mont(a), b);  // canonical r*s
+          for (int i = 0; i < 8; i++) rs[16 + i] = p.v[i];
+          ws->t_rsd = G1X::mul_affine(f1[2], p.v, 8);
+          break;
+        }
+        case 3: ws->t_sd2 = G2X::mul_affine(f2[1], ss, 8); break;
+        case 4: { G1X acc = G1X::identity(); for (uint32_t k = 0; k < world; k++) acc = G1X::add_ni(acc, parts[k].h); ws->sum_h = acc; break; }
+        case 5: { G1X acc = G1X::identity(); for (uint32_t k = 0; k < world; k++) acc = G1X::add_ni(acc, parts[k].l); ws->sum_l = acc; break; }
+        case 6: { G1X acc = G1X::identity(); for (uint32_t k = 0; k < world; k++) acc = G1X::add_ni(acc, parts[k].a); ws->sum_a = acc; break; }
+        case 7: { G1X acc = G1X::identity(); for (uint32_t k = 0; k < world; k++) acc = G1X::add_ni(acc, parts[k].b1); ws->sum_b1 = acc; break; }
+        case 8: { G2X acc = G2X::identity(); for (uint32_t k = 0; k < world; k++) acc = G2X::add_ni(acc, parts[k].b2); ws->sum_b2 = acc; break; }
+      }
+    });
+    // phase B: g_a, g1_b, g2_b
+    launch<k_final_b, 1>(st_, 3, ZKB_LAMBDA(size_t role) {
+      switch ((int)role) {
+        case 0: ws->ga = G1X::madd_ni(G1X::madd_ni(G1X::add_ni(ws->t_rd, ws->sum_a), f1[3]), f1[0]); break;
+        case 1: ws->gb1 = G1X::madd_ni(G1X::madd_ni(G1X::add_ni(ws->t_sd, ws->sum_b1), f1[4]), f1[1]); break;
+        case 2: ws->gb2 = G2X::madd_ni(G2X::madd_ni(G2X::add_ni(ws->t_sd2, ws->sum_b2), f2[2]), f2[0]); break;
+      }
+    });
+    // phase C: s * g_a, r * g1_b
+    launch<k_final_c, 1>(st_, 2, ZKB_LAMBDA(size_t role) {
+      if (role == 0) ws->u1 = G1X::mul_xyzz(ws->ga, rs + 8, 8);
+      else ws->u2 = G1X::mul_xyzz(ws->gb1, rs, 8);
+    });
+    // phase D: affine outputs, canonical little-endian
+    launch<k_final_d, 1>(st_, 3, ZKB_LAMBDA(size_t role) {
+      const int NQ = Fq::N;
+      if (role == 0) {
+        G1A a = G1X::to_affine(ws->ga);
+        Fq x = Fq::from_mont(a.x), y = Fq::from_mont(a.y);
+        for (int i = 0; i < NQ; i++) { proof[i] = x.v[i]; proof[NQ + i] = y.v[i]; }
+      } else if (role == 1) {
+        G2A b = G2X::to_affine(ws->gb2);
+        Fq2 x = Fq2::from_mont(b.x), y = Fq2::from_mont(b.y);
+        for (int i = 0; i < NQ; i++) {
+          proof[2 * NQ + i] = x.c0.v[i]; proof[3 * NQ + i] = x.c1.v[i];
+          proof[4 * NQ + i] = y.c0.v[i]; proof[5 * NQ + i] = y.c1.v[i];
+        }
+      } else {
+        G1X cacc = G1X::add_ni(ws->u1, ws->u2);
+        cacc = G1X::add_ni(cacc, G1X::neg(ws->t_rsd));
+        cacc = G1X::add_ni(cacc, ws->sum_l);
+        cacc = G1X::add_ni(cacc, ws->sum_h);
+        G1A cc = G1X::to_affine(cacc);
+        Fq x = Fq::from_mont(cc.x), y = Fq::from_mont(cc.y);
+        for (int i = 0; i < NQ; i++) { proof[6 * NQ + i] = x.v[i]; proof[7 * NQ + i] = y.v[i]; }
+      }
+    });
+    tm.end();
+    d2h(st_, proof_out, proof, 8 * FQB);
+    stream_sync(st_);
+    std::vector<std::pair<const char*, double>> t2;
+    tm.collect(t2);
+    for (auto& e : t2) timings.push_back(e);
+  }
+
+  // ------------------------------------------------------------------------------ standalone MSM (tests / microbench)
+  DevBuf<uint8_t> msm_pts_;
+  DevBuf<Fr> msm_scalars_;
+  MsmPlan plan_misc_;
+
+  template <class F>
+  void msm_t(const uint8_t* points, const uint64_t* scalars, uint64_t n, uint8_t* out) {
+    typedef Affine<F> A;
+    typedef XYZZ<F> X;
+    StageTimer tm(st_);
+    msm_pts_.ensure(n * sizeof(A) + 16);
+    msm_scalars_.ensure(n + 1);
+    ws_result_.ensure(sizeof(X) + sizeof(A));
+    A* pts = (A*)msm_pts_.p;
+    h2d(st_, pts, points, n * sizeof(A));
+    h2d(st_, msm_scalars_.p, scalars, n * FRB);
+    pk_convert<F>(pts, n);
+    tm.begin("msm_plan");
+    plan_build(plan_misc_, msm_scalars_.p, n);
+    tm.end();
+    X* res = (X*)ws_result_.p;
+    tm.begin("msm_exec");
+    msm_exec<F>(plan_misc_, pts, res);
+    tm.end();
+    uint32_t* o = (uint32_t*)(ws_result_.p + sizeof(X));
+    launch<k_point_out, 1>(st_, 1, ZKB_LAMBDA(size_t) {
+      A a = X::to_affine(*res);
+      const int words = sizeof(A) / 4;
+      if (a.is_inf()) {
+        for (int i = 0; i < words; i++) o[i] = 0;
+        o[words - 1] = 0x40000000u;
+      } else {
+        A c{F::from_mont(a.x), F::from_mont(a.y)};
+        const uint32_t* raw = (const uint32_t*)&c;
+        for (int i = 0; i < words; i++) o[i] = raw[i];
+      }
+    });
+    d2h(st_, out, o, sizeof(A));
+    stream_sync(st_);
+    tm.collect(timings);
+  }
+  void msm(int group, const uint8_t* points, const uint64_t* scalars, uint64_t n, uint8_t* out) override {
+    if (group == 1) msm_t<Fq>(points, scalars, n, out);
+    else if (group == 2) msm_t<Fq2>(points, scalars, n, out);
+    else throw Error(ZKB_E_ARG, "group");
+  }
+
+  // ------------------------------------------------------------------------------ field ops
+  template <class F>
+  void field_op_t(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n) {
+    DevBuf<F> da(n), db(n), dc(n);
+    h2d(st_, da.p, a, n * sizeof(F));
+    if (b) h2d(st_, db.p, b, n * sizeof(F)); else dev_zero(st_, db.p, n * sizeof(F));
+    F* pa = da.p; F* pb = db.p; F* pc = dc.p;
+    launch<k_field_op>(st_, n, ZKB_LAMBDA(size_t t) {
+      F x = F::to_mont(pa[t]), y = F::to_mont(pb[t]), r;
+      switch (op) {
+        case 0: r = F::mul(x, y); break;
+        case 1: r = F::add(x, y); break;
+        case 2: r = F::sub(x, y); break;
+        default: r = F::inv(x); break;
+      }
+      pc[t] = F::from_mont(r);
+    });
+    d2h(st_, out, pc, n * sizeof(F));
+    stream_sync(st_);
+  }
+  void field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n) override {
+    if (op < 0 || op > 3) throw Error(ZKB_E_ARG, "op");
+    if (field == 0) field_op_t<Fr>(op, a, b, out, n);
+    else if (field == 1) field_op_t<Fq>(op, a, b, out, n);
+    else throw Error(ZKB_E_ARG, "field");
+  }
+
+  // ------------------------------------------------------------------------------ setup (see setup.cuh)
+  template <class F> void fb_build(FixedBase<F>& fb, Affine<F> stdgen, const uint32_t* gk);
+  template <class F> void fb_emit(const FixedBase<F>& fb, const Fr* scalars, size_t count, uint32_t* dst);
+  size_t setup_size(uint64_t rh) override;
+  void setup(uint64_t rh, const uint64_t* trapdoor7, uint8_t* pk_out, size_t cap, size_t* len) override;
+
+ protected:
+  Stream st_;
+};
+
+}  // namespace zkb

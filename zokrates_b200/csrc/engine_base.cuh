@@ -1,0 +1,38 @@
+// Curve-independent interface of the proving engine (one instance per zkb_ctx).
+#pragma once
+#include <utility>
+#include <vector>
+#include "rt.cuh"
+
+namespace zkb {
+
+struct EngineBase {
+  virtual ~EngineBase() {}
+  virtual void sizes(uint64_t out[4]) = 0;
+  virtual uint64_t pk_load(const uint8_t* pk, size_t len, uint32_t rank, uint32_t world) = 0;
+  virtual void pk_info(uint64_t h, uint64_t out[4]) = 0;
+  virtual void pk_free(uint64_t h) = 0;
+  virtual uint64_t r1cs_load(uint64_t N, uint64_t ni, uint64_t nw, const uint64_t* const rowptr[3],
+                             const uint32_t* const col[3], const uint64_t* const val[3]) = 0;
+  virtual void r1cs_free(uint64_t h) = 0;
+  virtual void set_assignment(uint64_t r1cs, const uint64_t* z) = 0;
+  virtual void prove_partial(uint64_t pk, uint64_t r1cs, const uint64_t* z, uint8_t* partial_out) = 0;
+  virtual void finalize(uint64_t pk, const uint8_t* partials, uint32_t world, const uint64_t* r, const uint64_t* s,
+                        uint8_t* proof_out) = 0;
+  virtual void msm(int group, const uint8_t* points, const uint64_t* scalars, uint64_t n, uint8_t* out) = 0;
+  virtual void ntt(uint64_t* data, uint32_t log_n, int inverse, int coset) = 0;
+  virtual void witness_map(uint64_t r1cs, const uint64_t* z, uint64_t* h_out, uint64_t cap) = 0;
+  virtual void field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n) = 0;
+  virtual size_t setup_size(uint64_t r1cs) = 0;
+  virtual void setup(uint64_t r1cs, const uint64_t* trapdoor7, uint8_t* pk_out, size_t cap, size_t* len) = 0;
+  std::vector<std::pair<const char*, double>> timings;
+};
+
+
+// one translation unit per curve (engine_bn254.cu / engine_bls12_381.cu)
+EngineBase* make_engine_bn254(Stream st);
+EngineBase* make_engine_bls12_381(Stream st);
+size_t partial_bytes_bn254();
+size_t partial_bytes_bls12_381();
+
+}  // namespace zkb

@@ -1,0 +1,234 @@
+// Multi-scalar multiplication sum_i s_i * P_i (Pippenger bucket method) for G1 and G2.
+//
+// Replaces ark-ec 0.3.0 `VariableBaseMSM::multi_scalar_mul` (external, Cargo.lock:146) as called
+// five times per proof by ark-groth16's prover (reached from
+// /root/reference/zokrates_ark/src/groth16.rs:44).  The result
+// is a group element, so any window size / digit encoding gives the same affine point as ark's
+// (unsigned windows, c = ln-rule) — only the schedule is redesigned for the GPU:
+//
+//   digits   : signed c-bit digits per scalar (halves the bucket count), histogram per bucket
+//   scan     : exclusive prefix sum -> bucket offsets
+//   scatter  : counting sort of (point index, sign) by (window, bucket)
+//   accumulate: the sorted list is cut into FIXED-SIZE chunks, one thread per chunk, so the load is
+//              balanced for any scalar distribution (real witnesses are mostly 0/1).
+//              A bucket wholly inside a chunk is written directly; a bucket cut by a chunk border
+//              is deferred as a partial sum to the next (much smaller) level, which runs the same
+//              segmented reduction on XYZZ partials.
+//   bucket tree + window Horner: sum_j j * B_j per window by an L-ary tree, then 2^(c w) weights.
+//
+// One "plan" (digits/sort) is reused for every point vector that shares the scalars: a_query,
+// b_g1_query, b_g2_query and l_query all pair with the same assignment vector.
+#pragma once
+#include "ec.cuh"
+
+namespace zkb {
+
+static constexpr uint32_t MSM_NONE = 0xFFFFFFFFu;   // zero digit / empty slot
+static constexpr uint32_t MSM_NEG = 0x80000000u;
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ uint32_t zkb_atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+#else
+inline uint32_t zkb_atomic_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+#endif
+
+struct MsmShape {
+  uint32_t n;        // number of (scalar, point) pairs
+  uint32_t c;        // window bits
+  uint32_t W;        // windows
+  uint32_t B;        // buckets per window = 2^(c-1)
+};
+
+ZKB_HD uint32_t scalar_bits(const uint32_t* s, uint32_t lo, uint32_t cnt) {
+  // bits [lo, lo+cnt) of a 256-bit little-endian scalar, cnt <= 31
+  uint32_t limb = lo >> 5, sh = lo & 31;
+  uint64_t v = limb < 8 ? s[limb] : 0;
+  if (limb + 1 < 8) v |= (uint64_t)s[limb + 1] << 32;
+  return (uint32_t)(v >> sh) & ((1u << cnt) - 1u);
+}
+
+// ---- digits + histogram: one thread per scalar -------------------------------------------------
+// digits[w * n + i] = (|d| - 1) | sign, or MSM_NONE when d == 0.
+ZKB_HDN inline void msm_digits_body(MsmShape sh, const uint32_t* scalars /* n x 8, canonical */, uint32_t* digits,
+                                    uint32_t* counts, uint32_t i) {
+  if (i >= sh.n) return;
+  uint32_t s[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) s[k] = scalars[(size_t)i * 8 + k];
+  uint32_t carry = 0;
+  const uint32_t full = 1u << sh.c, half = sh.B;
+  for (uint32_t w = 0; w < sh.W; w++) {
+    uint32_t d = scalar_bits(s, w * sh.c, sh.c) + carry;
+    uint32_t code;
+    if (d == 0) {
+      code = MSM_NONE;
+      carry = 0;
+    } else if (d > half) {
+      code = (full - d - 1) | MSM_NEG;  // digit d - 2^c < 0, magnitude 2^c - d in [1, 2^(c-1) - 1]
+      carry = 1;
+      if (full - d == 0) {              // d == 2^c: digit 0, carry 1
+        code = MSM_NONE;
+      }
+    } else {
+      code = d - 1;
+      carry = 0;
+    }
+    digits[(size_t)w * sh.n + i] = code;
+    if (code != MSM_NONE) zkb_atomic_add(&counts[w * sh.B + (code & ~MSM_NEG)], 1);
+  }
+}
+
+// ---- scatter: one thread per (window, scalar) --------------------------------------------------
+ZKB_HDN inline void msm_scatter_body(MsmShape sh, const uint32_t* digits, const uint32_t* offsets, uint32_t* cursor,
+                                     uint32_t* sorted, size_t t) {
+  if (t >= (size_t)sh.n * sh.W) return;
+  uint32_t code = digits[t];
+  if (code == MSM_NONE) return;
+  uint32_t w = (uint32_t)(t / sh.n), i = (uint32_t)(t % sh.n);
+  uint32_t key = w * sh.B + (code & ~MSM_NEG);
+  uint32_t pos = zkb_atomic_add(&cursor[key], 1);
+  sorted[offsets[key] + pos] = i | (code & MSM_NEG);
+}
+
+// ---- level-1 accumulate: affine points, keys implied by the offsets array -----------------------
+// Thread t owns sorted positions [t*T, (t+1)*T).  Deferred partials go to slots 2t (first segment)
+// and 2t+1 (last segment) of (pkey, pval); unused slots get MSM_NONE.
+template <class F>
+ZKB_HDN inline void msm_accum1_body(uint32_t nbuckets, uint32_t T, const uint32_t* offsets, const uint32_t* sorted,
+                                    const Affine<F>* points, XYZZ<F>* buckets, uint32_t* pkey, XYZZ<F>* pval,
+                                    uint32_t nthreads, uint32_t t) {
+  if (t >= nthreads) return;
+  const uint32_t M = offsets[nbuckets];
+  uint32_t k0 = MSM_NONE, k1 = MSM_NONE;
+  uint64_t start64 = (uint64_t)t * T;
+  if (start64 < M) {
+    uint32_t pos = (uint32_t)start64;
+    uint32_t end = (M - pos > T) ? pos + T : M;
+    // bucket containing pos: largest b with offsets[b] <= pos  (offsets is non-decreasing)
+    uint32_t lo = 0, hi = nbuckets;  // invariant offsets[lo] <= pos < offsets[hi]
+    while (hi - lo > 1) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (offsets[mid] <= pos) lo = mid; else hi = mid;
+    }
+    uint32_t b = lo;
+    const uint32_t cstart = pos;
+    while (pos < end) {
+      while (offsets[b + 1] <= pos) b++;  // skip empty buckets
+      uint32_t bstart = offsets[b], bend = offsets[b + 1];
+      uint32_t seg_end = bend < end ? bend : end;
+      XYZZ<F> acc = XYZZ<F>::identity();
+      for (uint32_t p = pos; p < seg_end; p++) {
+        uint32_t e = sorted[p];
+        Affine<F> q = points[e & ~MSM_NEG];
+        if (e & MSM_NEG) q.y = F::neg(q.y);
+        acc = XYZZ<F>::madd(acc, q);
+      }
+      bool complete = bstart >= cstart && bend <= end;
+      if (complete) {
+        buckets[b] = acc;
+      } else if (bstart < cstart) {  // continues from the previous chunk: first segment
+        k0 = b;
+        pval[2 * (size_t)t] = acc;
+      } else {                       // runs into the next chunk: last segment
+        k1 = b;
+        pval[2 * (size_t)t + 1] = acc;
+      }
+      pos = seg_end;
+    }
+  }
+  pkey[2 * (size_t)t] = k0;
+  pkey[2 * (size_t)t + 1] = k1;
+}
+
+// ---- level >= 2: segmented reduction over (key, XYZZ) entries with holes ------------------------
+// Chunk t owns entries [t*T - 1, (t+1)*T - 1) (shifted by one so that the pair "last of chunk u /
+// first of chunk u+1" emitted by the level below is never cut again).  Same-key entries are
+// separated by at most one MSM_NONE hole, so two-entry look-behind/ahead decides
+// whether a run is complete.
+template <class F>
+ZKB_HDN inline void msm_accum2_body(uint32_t L, uint32_t T, const uint32_t* key, const XYZZ<F>* val, XYZZ<F>* buckets,
+                                    uint32_t* okey, XYZZ<F>* oval, uint32_t nthreads, uint32_t t) {
+  if (t >= nthreads) return;
+  uint64_t s64 = (uint64_t)t * T;
+  uint32_t s = s64 == 0 ? 0 : (uint32_t)(s64 - 1);
+  uint64_t e64 = s64 + T - 1;
+  uint32_t e = e64 < L ? (uint32_t)e64 : L;
+  uint32_t k0 = MSM_NONE, k1 = MSM_NONE;
+  // key just left of the chunk (skipping one hole)
+  uint32_t left = MSM_NONE;
+  if (s >= 1) {
+    left = key[s - 1];
+    if (left == MSM_NONE && s >= 2) left = key[s - 2];
+  }
+  uint32_t right = MSM_NONE;
+  if (e < L) {
+    right = key[e];
+    if (right == MSM_NONE && e + 1 < L) right = key[e + 1];
+  }
+  uint32_t cur = MSM_NONE;
+  XYZZ<F> acc = XYZZ<F>::identity();
+  bool first = true;  // cur is the first run of this chunk
+  for (uint32_t p = s; p <= e; p++) {
+    uint32_t k = (p < e) ? key[p] : MSM_NONE - 1;  // sentinel flushes the last run
+    if (p < e && k == MSM_NONE) continue;
+    if (k != cur) {
+      if (cur != MSM_NONE) {
+        bool last = (p == e);
+        bool open_left = first && left == cur;
+        bool open_right = last && right == cur;
+        if (!open_left && !open_right) {
+          buckets[cur] = acc;
+        } else if (open_left) {
+          k0 = cur;
+          oval[2 * (size_t)t] = acc;
+        } else {
+          k1 = cur;
+          oval[2 * (size_t)t + 1] = acc;
+        }
+        first = false;
+      }
+      cur = k;
+      acc = XYZZ<F>::identity();
+    }
+    if (p < e) acc = XYZZ<F>::add_ni(acc, val[p]);
+  }
+  okey[2 * (size_t)t] = k0;
+  okey[2 * (size_t)t + 1] = k1;
+}
+
+// ---- bucket tree: per window sum_j (j+1) * bucket[j] via (A, Wt) pairs --------------------------
+// Level `lvl` (0-based) combines groups of Lr = 2^lr children.  A child at level lvl covers
+// S = Lr^lvl original buckets.  A = plain sum, Wt = sum (index - base) * bucket.
+template <class F>
+ZKB_HDN inline void msm_tree_body(uint32_t W, uint32_t cnt_in, uint32_t lr, uint32_t lvl, const XYZZ<F>* inA,
+                                  const XYZZ<F>* inWt, XYZZ<F>* outA, XYZZ<F>* outWt, uint32_t t) {
+  const uint32_t Lr = 1u << lr;
+  const uint32_t cnt_out = (cnt_in + Lr - 1) >> lr;
+  if (t >= W * cnt_out) return;
+  uint32_t w = t / cnt_out, k = t % cnt_out;
+  const XYZZ<F>* A = inA + (size_t)w * cnt_in;
+  uint32_t lo = k << lr;
+  uint32_t hi = lo + Lr < cnt_in ? lo + Lr : cnt_in;
+  XYZZ<F> run = XYZZ<F>::identity(), wrel = XYZZ<F>::identity(), wsum = XYZZ<F>::identity();
+  for (uint32_t i = hi; i-- > lo;) {
+    run = XYZZ<F>::add_ni(run, A[i]);
+    if (i > lo) wrel = XYZZ<F>::add_ni(wrel, run);
+    if (lvl > 0) wsum = XYZZ<F>::add_ni(wsum, inWt[(size_t)w * cnt_in + i]);
+  }
+  for (uint32_t d = 0; d < lr * lvl; d++) wrel = XYZZ<F>::dbl_ni(wrel);  // times S = 2^(lr*lvl)
+  outA[(size_t)w * cnt_out + k] = run;
+  outWt[(size_t)w * cnt_out + k] = XYZZ<F>::add_ni(wsum, wrel);
+}
+
+// ---- window combine: result = sum_w 2^(c w) (Wt_w + A_w)  (single thread) ------------------------
+template <class F>
+ZKB_HDN inline void msm_horner_body(uint32_t W, uint32_t c, const XYZZ<F>* A, const XYZZ<F>* Wt, XYZZ<F>* out) {
+  XYZZ<F> acc = XYZZ<F>::identity();
+  for (uint32_t w = W; w-- > 0;) {
+    for (uint32_t d = 0; d < c; d++) acc = XYZZ<F>::dbl_ni(acc);
+    acc = XYZZ<F>::add_ni(acc, XYZZ<F>::add_ni(A[w], Wt[w]));
+  }
+  *out = acc;
+}
+
+}  // namespace zkb

@@ -1,0 +1,154 @@
+// Thin runtime layer: device memory, copies and kernel launches.
+//
+// Product build (nvcc, sm_100a): every `launch<Tag>(n, fn)` is a real kernel on the engine's CUDA
+// stream; failures surface as zkb::Error (never a silent CPU path).
+// Test build (-DZKB_EMU, plain g++): the same orchestration code runs the kernel bodies in a host
+// loop so tests/host_emu can check indexing logic without a GPU.  libzkb200.so is never built with
+// ZKB_EMU.
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdexcept>
+#include <string>
+#include "hd.cuh"
+#include "zkb.h"  // status codes (include/zkb.h)
+
+#if !defined(ZKB_EMU)
+#include <cuda_runtime.h>
+#endif
+
+namespace zkb {
+
+struct Error : public std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+
+#if !defined(ZKB_EMU)
+
+#define ZKB_CUDA(expr)                                                                                   \
+  do {                                                                                                    \
+    cudaError_t _e = (expr);                                                                              \
+    if (_e != cudaSuccess)                                                                                \
+      throw ::zkb::Error(_e == cudaErrorMemoryAllocation ? ZKB_E_OOM : ZKB_E_CUDA,          \
+                         std::string(#expr) + ": " + cudaGetErrorString(_e));                             \
+  } while (0)
+
+struct Stream {
+  cudaStream_t s = nullptr;
+};
+
+template <class Tag, class Fn>
+__global__ void zkb_kernel(size_t n, Fn fn) {
+  size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid < n) fn(tid);
+}
+
+#define ZKB_LAMBDA [=] __device__
+
+inline uint64_t& launch_counter() {
+  static uint64_t c = 0;
+  return c;
+}
+
+template <class Tag, int BLOCK = 128, class Fn>
+inline void launch(Stream st, size_t n, Fn fn) {
+  if (n == 0) return;
+  launch_counter()++;
+  size_t blocks = (n + BLOCK - 1) / BLOCK;
+  if (blocks > 0x7fffffffull) throw Error(ZKB_E_ARG, "grid too large");
+  zkb_kernel<Tag, Fn><<<(unsigned)blocks, BLOCK, 0, st.s>>>(n, fn);
+  ZKB_CUDA(cudaGetLastError());
+}
+
+inline void* dev_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0) bytes = 16;
+  ZKB_CUDA(cudaMalloc(&p, bytes));
+  return p;
+}
+inline void dev_free(void* p) {
+  if (p) cudaFree(p);
+}
+inline void h2d(Stream st, void* dst, const void* src, size_t bytes) {
+  if (bytes) ZKB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st.s));
+}
+inline void d2h(Stream st, void* dst, const void* src, size_t bytes) {
+  if (bytes) ZKB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st.s));
+}
+inline void d2d(Stream st, void* dst, const void* src, size_t bytes) {
+  if (bytes) ZKB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st.s));
+}
+inline void dev_zero(Stream st, void* p, size_t bytes) {
+  if (bytes) ZKB_CUDA(cudaMemsetAsync(p, 0, bytes, st.s));
+}
+inline void dev_fill_ff(Stream st, void* p, size_t bytes) {
+  if (bytes) ZKB_CUDA(cudaMemsetAsync(p, 0xff, bytes, st.s));
+}
+inline void stream_sync(Stream st) { ZKB_CUDA(cudaStreamSynchronize(st.s)); }
+
+#else  // ------------------------------------------------------------------ host emulation (tests)
+
+struct Stream {
+  int s = 0;
+};
+#define ZKB_LAMBDA [=]
+inline uint64_t& launch_counter() {
+  static uint64_t c = 0;
+  return c;
+}
+template <class Tag, int BLOCK = 128, class Fn>
+inline void launch(Stream, size_t n, Fn fn) {
+  if (n) launch_counter()++;
+  for (size_t tid = 0; tid < n; tid++) fn(tid);
+}
+inline void* dev_alloc(size_t bytes) {
+  void* p = malloc(bytes ? bytes : 16);
+  if (!p) throw Error(ZKB_E_OOM, "malloc");
+  return p;
+}
+inline void dev_free(void* p) { free(p); }
+inline void h2d(Stream, void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
+inline void d2h(Stream, void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
+inline void d2d(Stream, void* dst, const void* src, size_t bytes) { memmove(dst, src, bytes); }
+inline void dev_zero(Stream, void* p, size_t bytes) { memset(p, 0, bytes); }
+inline void dev_fill_ff(Stream, void* p, size_t bytes) { memset(p, 0xff, bytes); }
+inline void stream_sync(Stream) {}
+
+#endif
+
+// RAII device buffer
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t count = 0;
+  DevBuf() {}
+  explicit DevBuf(size_t n) { alloc(n); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), count(o.count) { o.p = nullptr; o.count = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; count = o.count; o.p = nullptr; o.count = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void alloc(size_t n) {
+    release();
+    p = (T*)dev_alloc(n * sizeof(T));
+    count = n;
+  }
+  void ensure(size_t n) {
+    if (n > count) alloc(n);
+  }
+  void release() {
+    dev_free(p);
+    p = nullptr;
+    count = 0;
+  }
+  size_t bytes() const { return count * sizeof(T); }
+};
+
+}  // namespace zkb
