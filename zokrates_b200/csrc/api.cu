@@ -166,11 +166,7 @@ static void prove_common(zkb_ctx* ctx, uint64_t pk, uint64_t r1cs, const uint64_
                          uint8_t* proof_out, size_t cap) {
   if (!r || !s || !proof_out) throw Error(ZKB_E_ARG, "null argument");
   check_proof_cap(ctx, cap);
-  uint64_t sz[4];
-  ctx->eng->sizes(sz);
-  std::vector<uint8_t> partial(sz[3]);
-  ctx->eng->prove_partial(pk, r1cs, z, partial.data());
-  ctx->eng->finalize(pk, partial.data(), 1, r, s, proof_out);
+  ctx->eng->prove_full(pk, r1cs, z, r, s, proof_out);
 }
 
 int32_t zkb_groth16_prove(zkb_ctx* ctx, uint64_t pk, uint64_t r1cs, const uint64_t* z, const uint64_t* r, const uint64_t* s,

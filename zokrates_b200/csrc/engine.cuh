@@ -11,6 +11,8 @@
 #include <map>
 #include <memory>
 #include <vector>
+#include <future>
+#include "fp64.cuh"
 #include "msm.cuh"
 #include "ntt.cuh"
 #include "rt.cuh"
@@ -136,6 +138,10 @@ struct CurveT {
   typedef Affine<Fq2> G2A;
   typedef XYZZ<Fq> G1X;
   typedef XYZZ<Fq2> G2X;
+  // host mirrors (64-bit limbs, identical memory layout) for the serial tail of the prover
+  typedef Fp64<FrP> HFr;
+  typedef Fp64<FqP> HFq;
+  typedef Fp2T<HFq> HFq2;
   static constexpr int FR_BITS = FrP::BITS;
   static constexpr int FQ_BYTES = FqP::N * 4;
 };
@@ -150,6 +156,14 @@ class Engine : public EngineBase {
   typedef typename C::G2A G2A;
   typedef typename C::G1X G1X;
   typedef typename C::G2X G2X;
+  typedef typename C::HFr HFr;
+  typedef typename C::HFq HFq;
+  typedef typename C::HFq2 HFq2;
+  typedef Affine<HFq> HG1A;
+  typedef Affine<HFq2> HG2A;
+  typedef XYZZ<HFq> HG1X;
+  typedef XYZZ<HFq2> HG2X;
+  static_assert(sizeof(HG1X) == sizeof(G1X) && sizeof(HG2X) == sizeof(G2X) && sizeof(HG1A) == sizeof(G1A), "host/device layout");
   static constexpr size_t FRB = 32, FQB = C::FQ_BYTES, G1B = 2 * FQB, G2B = 4 * FQB;
   static_assert(sizeof(Fr) == 32 && sizeof(G1A) == G1B && sizeof(G2A) == G2B, "layout");
 
@@ -400,7 +414,7 @@ class Engine : public EngineBase {
   }
 
   // ------------------------------------------------------------------------------ MSM
-  DevBuf<uint8_t> ws_buckets_, ws_val_[2], ws_tree_[4], ws_result_;
+  DevBuf<uint8_t> ws_buckets_, ws_val_[2], ws_tree_[4];
   DevBuf<uint32_t> ws_key_[2];
 
   void plan_build(MsmPlan& pl, const Fr* scalars, uint64_t n) {
@@ -436,9 +450,9 @@ class Engine : public EngineBase {
   }
 
   template <class F>
-  void msm_exec(const MsmPlan& pl, const Affine<F>* pts, XYZZ<F>* result) {
+  void msm_exec(const MsmPlan& pl, const Affine<F>* pts, XYZZ<F>* win_out /* 2 W entries */) {
     typedef XYZZ<F> X;
-    if (pl.sh.n == 0) { dev_zero(st_, result, sizeof(X)); return; }
+    if (pl.sh.n == 0) return;
     const uint32_t NB = pl.nbuckets, W = pl.sh.W, B = pl.sh.B, c = pl.sh.c;
     ws_buckets_.ensure((size_t)NB * sizeof(X));
     X* buckets = (X*)ws_buckets_.p;
@@ -476,8 +490,20 @@ class Engine : public EngineBase {
       inA = oA; inWt = oW; cnt = cnt_out; lvl++;
       pp ^= 2;
     }
-    const X* fA = inA; const X* fW = inWt;
-    launch<k_msm_horner, 1>(st_, 1, ZKB_LAMBDA(size_t) { msm_horner_body<F>(W, c, fA, fW, result); });
+    // window sums (A_w, Wt_w) -> caller's slot; the 2^(c w) Horner runs on the host (see fp64.cuh)
+    d2d(st_, win_out, inA, (size_t)W * sizeof(X));
+    d2d(st_, win_out + W, inWt, (size_t)W * sizeof(X));
+  }
+
+  // result = sum_w 2^(c w) (A_w + Wt_w) on the host
+  template <class HX>
+  static HX host_horner(const HX* win, uint32_t W, uint32_t c) {
+    HX acc = HX::identity();
+    for (uint32_t w = W; w-- > 0;) {
+      for (uint32_t d = 0; d < c; d++) acc = HX::dbl(acc);
+      acc = HX::add(acc, HX::add(win[w], win[W + w]));
+    }
+    return acc;
   }
 
   // ------------------------------------------------------------------------------ proving key
@@ -489,6 +515,8 @@ class Engine : public EngineBase {
     DevBuf<G2A> b2;
     DevBuf<G1A> fixed1;                          // alpha1, beta1, delta1, a_query[0], b_g1_query[0]
     DevBuf<G2A> fixed2;                          // beta2, delta2, b_g2_query[0]
+    HG1A h_fixed1[5];                            // host copies (Montgomery form) for the serial tail
+    HG2A h_fixed2[3];
   };
   std::map<uint64_t, std::unique_ptr<Pk>> pks_;
   Pk& get_pk(uint64_t h) {
@@ -584,6 +612,8 @@ class Engine : public EngineBase {
       uint64_t j0 = p->lo > shift ? p->lo : shift;
       if (j0 < p->hi) pk_convert<Fq>(p->l.p + (j0 - p->lo), p->hi - j0);
     }
+    d2h(st_, p->h_fixed1, p->fixed1.p, 5 * G1B);
+    d2h(st_, p->h_fixed2, p->fixed2.p, 3 * G2B);
     stream_sync(st_);
     uint64_t h = next_handle_++;
     pks_[h] = std::move(p);
@@ -597,15 +627,22 @@ class Engine : public EngineBase {
 
   // ------------------------------------------------------------------------------ prove
   MsmPlan plan_z_, plan_h_;
-  DevBuf<Partial> d_partial_;
   DevBuf<Fr> scratch_a_, scratch_b_;
+  DevBuf<uint8_t> d_win_;
+  static constexpr uint32_t MAXW = 72;  // windows per MSM never exceed ceil(256 / 4)
+
+  struct HostPartial {  // same layout as Partial
+    HG1X h, l, a, b1;
+    HG2X b2;
+  };
+  static_assert(sizeof(HostPartial) == sizeof(Partial), "partial layout");
 
   void prove_partial(uint64_t pkh, uint64_t rh, const uint64_t* z, uint8_t* partial_out) override {
     Pk& pk = get_pk(pkh);
     R1cs& r = get_r1cs(rh);
     const size_t n = (size_t)1 << r.log_n;
     if (pk.m != r.m || pk.ni != r.ni) throw Error(ZKB_E_ARG, "proving key does not match the R1CS (variable counts)");
-    if (pk.hl + 1 != n && !(n == 1 && pk.hl == 0)) throw Error(ZKB_E_ARG, "proving key does not match the R1CS (domain size)");
+    if (pk.hl + 1 != n) throw Error(ZKB_E_ARG, "proving key does not match the R1CS (domain size)");
     StageTimer tm(st_);
     if (z) {
       tm.begin("h2d_z");
@@ -616,125 +653,115 @@ class Engine : public EngineBase {
       throw Error(ZKB_E_ARG, "no resident assignment");
     }
     witness_map_dev(r, tm);
-    d_partial_.ensure(1);
-    Partial* out = d_partial_.p;
+    const size_t slot1 = 2 * MAXW * sizeof(G1X), slot2 = 2 * MAXW * sizeof(G2X);
+    d_win_.ensure(4 * slot1 + slot2);
+    G1X* w_h = (G1X*)d_win_.p;
+    G1X* w_l = (G1X*)(d_win_.p + slot1);
+    G1X* w_a = (G1X*)(d_win_.p + 2 * slot1);
+    G1X* w_b1 = (G1X*)(d_win_.p + 3 * slot1);
+    G2X* w_b2 = (G2X*)(d_win_.p + 4 * slot1);
     tm.begin("msm_plan_h");
     plan_build(plan_h_, r.h.p + pk.hlo, pk.hhi - pk.hlo);
     tm.end();
     tm.begin("msm_h");
-    msm_exec<Fq>(plan_h_, pk.h.p, &out->h);
+    msm_exec<Fq>(plan_h_, pk.h.p, w_h);
     tm.end();
     tm.begin("msm_plan_z");
     plan_build(plan_z_, r.z_canon.p + 1 + pk.lo, pk.hi - pk.lo);
     tm.end();
     tm.begin("msm_l");
-    msm_exec<Fq>(plan_z_, pk.l.p, &out->l);
+    msm_exec<Fq>(plan_z_, pk.l.p, w_l);
     tm.end();
     tm.begin("msm_a");
-    msm_exec<Fq>(plan_z_, pk.a.p, &out->a);
+    msm_exec<Fq>(plan_z_, pk.a.p, w_a);
     tm.end();
     tm.begin("msm_b1");
-    msm_exec<Fq>(plan_z_, pk.b1.p, &out->b1);
+    msm_exec<Fq>(plan_z_, pk.b1.p, w_b1);
     tm.end();
     tm.begin("msm_b2");
-    msm_exec<Fq2>(plan_z_, pk.b2.p, &out->b2);
+    msm_exec<Fq2>(plan_z_, pk.b2.p, w_b2);
     tm.end();
-    d2h(st_, partial_out, out, sizeof(Partial));
+    std::vector<uint8_t> hw(4 * slot1 + slot2);
+    tm.begin("d2h_windows");
+    d2h(st_, hw.data(), d_win_.p, hw.size());
+    tm.end();
     stream_sync(st_);
     tm.collect(timings);
+    HostPartial hp;
+    auto hor1 = [&](size_t k, const MsmPlan& pl) {
+      return pl.sh.n ? host_horner<HG1X>((const HG1X*)(hw.data() + k * slot1), pl.sh.W, pl.sh.c) : HG1X::identity();
+    };
+    hp.h = hor1(0, plan_h_); hp.l = hor1(1, plan_z_); hp.a = hor1(2, plan_z_); hp.b1 = hor1(3, plan_z_);
+    hp.b2 = plan_z_.sh.n ? host_horner<HG2X>((const HG2X*)(hw.data() + 4 * slot1), plan_z_.sh.W, plan_z_.sh.c)
+                         : HG2X::identity();
+    memcpy(partial_out, &hp, sizeof hp);
   }
 
-  struct FinalWs {
-    G1X t_rd, t_sd, t_rsd, ga, gb1, u1, u2, sum_h, sum_l, sum_a, sum_b1;
-    G2X t_sd2, gb2, sum_b2;
+  // the four scalar multiplications that only need (pk, r, s): computed while the GPU works
+  struct FixedMults {
+    HG1X rd, sd, rsd;
+    HG2X sd2;
   };
-  DevBuf<FinalWs> d_final_;
-  DevBuf<Partial> d_parts_;
-  DevBuf<uint32_t> d_rs_;
-  DevBuf<uint32_t> d_proof_;
+  static FixedMults fixed_mults(const Pk& pk, const uint32_t* r, const uint32_t* s) {
+    FixedMults f;
+    HFr a, b;
+    memcpy(a.v, r, 32); memcpy(b.v, s, 32);
+    HFr rs = HFr::mul(HFr::to_mont(a), b);  // canonical r * s
+    f.rd = HG1X::mul_affine(pk.h_fixed1[2], r, 8);
+    f.sd = HG1X::mul_affine(pk.h_fixed1[2], s, 8);
+    f.rsd = HG1X::mul_affine(pk.h_fixed1[2], (const uint32_t*)rs.v, 8);
+    f.sd2 = HG2X::mul_affine(pk.h_fixed2[1], s, 8);
+    return f;
+  }
+
+  void finalize_with(const Pk& pk, const FixedMults& fm, const uint8_t* partials, uint32_t world, const uint32_t* r,
+                     const uint32_t* s, uint8_t* proof_out) {
+    HostPartial sum;
+    sum.h = HG1X::identity(); sum.l = HG1X::identity(); sum.a = HG1X::identity(); sum.b1 = HG1X::identity();
+    sum.b2 = HG2X::identity();
+    for (uint32_t k = 0; k < world; k++) {
+      HostPartial p;
+      memcpy(&p, partials + (size_t)k * sizeof(HostPartial), sizeof p);
+      sum.h = HG1X::add(sum.h, p.h); sum.l = HG1X::add(sum.l, p.l); sum.a = HG1X::add(sum.a, p.a);
+      sum.b1 = HG1X::add(sum.b1, p.b1); sum.b2 = HG2X::add(sum.b2, p.b2);
+    }
+    // A = r d1 + a_0 + <a, z> + alpha1 ; B1, B2 likewise (fixed1: alpha1, beta1, delta1, a_0, b1_0; fixed2: beta2, delta2, b2_0)
+    HG1X ga = HG1X::madd(HG1X::madd(HG1X::add(fm.rd, sum.a), pk.h_fixed1[3]), pk.h_fixed1[0]);
+    HG1X gb1 = HG1X::madd(HG1X::madd(HG1X::add(fm.sd, sum.b1), pk.h_fixed1[4]), pk.h_fixed1[1]);
+    HG2X gb2 = HG2X::madd(HG2X::madd(HG2X::add(fm.sd2, sum.b2), pk.h_fixed2[2]), pk.h_fixed2[0]);
+    // C = s A + r B1 - r s d1 + L + H
+    HG1X gc = HG1X::add(HG1X::mul_xyzz(ga, s, 8), HG1X::mul_xyzz(gb1, r, 8));
+    gc = HG1X::add(gc, HG1X::neg(fm.rsd));
+    gc = HG1X::add(gc, sum.l);
+    gc = HG1X::add(gc, sum.h);
+    HG1A pa = HG1X::to_affine(ga), pc = HG1X::to_affine(gc);
+    HG2A pb = HG2X::to_affine(gb2);
+    auto put = [&](size_t slot, const HFq& v) { HFq c = HFq::from_mont(v); memcpy(proof_out + slot * FQB, c.v, FQB); };
+    put(0, pa.x); put(1, pa.y); put(2, pb.x.c0); put(3, pb.x.c1); put(4, pb.y.c0); put(5, pb.y.c1); put(6, pc.x); put(7, pc.y);
+  }
 
   void finalize(uint64_t pkh, const uint8_t* partials, uint32_t world, const uint64_t* r, const uint64_t* s,
                 uint8_t* proof_out) override {
     Pk& pk = get_pk(pkh);
     if (world == 0) throw Error(ZKB_E_ARG, "world");
-    StageTimer tm(st_);
-    d_parts_.ensure(world); d_final_.ensure(1); d_rs_.ensure(24); d_proof_.ensure(8 * FQB / 4);
-    h2d(st_, d_parts_.p, partials, world * sizeof(Partial));
-    h2d(st_, d_rs_.p, r, 32);
-    h2d(st_, d_rs_.p + 8, s, 32);
-    const Partial* parts = d_parts_.p;
-    FinalWs* ws = d_final_.p;
-    uint32_t* rs = d_rs_.p;
-    const G1A* f1 = pk.fixed1.p;
-    const G2A* f2 = pk.fixed2.p;
-    uint32_t* proof = d_proof_.p;
-    tm.begin("final_combine");
-    // phase A: independent scalar multiplications and the cross-rank sums, one thread-block each
-    launch<k_final_a, 1>(st_, 9, ZKB_LAMBDA(size_t role) {
-      const uint32_t* rr = rs;
-      const uint32_t* ss = rs + 8;
-      switch ((int)role) {
-        case 0: ws->t_rd = G1X::mul_affine(f1[2], rr, 8); break;
-        case 1: ws->t_sd = G1X::mul_affine(f1[2], ss, 8); break;
-        case 2: {
-          Fr a, b;
-          for (int i = 0; i < 8; i++) { a.v[i] = rr[i]; b.v[i] = ss[i]; }
-          Fr p = Fr::mul(Fr::to_mont(a), b);  // canonical r*s
-          for (int i = 0; i < 8; i++) rs[16 + i] = p.v[i];
-          ws->t_rsd = G1X::mul_affine(f1[2], p.v, 8);
-          break;
-        }
-        case 3: ws->t_sd2 = G2X::mul_affine(f2[1], ss, 8); break;
-        case 4: { G1X acc = G1X::identity(); for (uint32_t k = 0; k < world; k++) acc = G1X::add_ni(acc, parts[k].h); ws->sum_h = acc; break; }
-        case 5: { G1X acc = G1X::identity(); for (uint32_t k = 0; k < world; k++) acc = G1X::add_ni(acc, parts[k].l); ws->sum_l = acc; break; }
-        case 6: { G1X acc = G1X::identity(); for (uint32_t k = 0; k < world; k++) acc = G1X::add_ni(acc, parts[k].a); ws->sum_a = acc; break; }
-        case 7: { G1X acc = G1X::identity(); for (uint32_t k = 0; k < world; k++) acc = G1X::add_ni(acc, parts[k].b1); ws->sum_b1 = acc; break; }
-        case 8: { G2X acc = G2X::identity(); for (uint32_t k = 0; k < world; k++) acc = G2X::add_ni(acc, parts[k].b2); ws->sum_b2 = acc; break; }
-      }
-    });
-    // phase B: g_a, g1_b, g2_b
-    launch<k_final_b, 1>(st_, 3, ZKB_LAMBDA(size_t role) {
-      switch ((int)role) {
-        case 0: ws->ga = G1X::madd_ni(G1X::madd_ni(G1X::add_ni(ws->t_rd, ws->sum_a), f1[3]), f1[0]); break;
-        case 1: ws->gb1 = G1X::madd_ni(G1X::madd_ni(G1X::add_ni(ws->t_sd, ws->sum_b1), f1[4]), f1[1]); break;
-        case 2: ws->gb2 = G2X::madd_ni(G2X::madd_ni(G2X::add_ni(ws->t_sd2, ws->sum_b2), f2[2]), f2[0]); break;
-      }
-    });
-    // phase C: s * g_a, r * g1_b
-    launch<k_final_c, 1>(st_, 2, ZKB_LAMBDA(size_t role) {
-      if (role == 0) ws->u1 = G1X::mul_xyzz(ws->ga, rs + 8, 8);
-      else ws->u2 = G1X::mul_xyzz(ws->gb1, rs, 8);
-    });
-    // phase D: affine outputs, canonical little-endian
-    launch<k_final_d, 1>(st_, 3, ZKB_LAMBDA(size_t role) {
-      const int NQ = Fq::N;
-      if (role == 0) {
-        G1A a = G1X::to_affine(ws->ga);
-        Fq x = Fq::from_mont(a.x), y = Fq::from_mont(a.y);
-        for (int i = 0; i < NQ; i++) { proof[i] = x.v[i]; proof[NQ + i] = y.v[i]; }
-      } else if (role == 1) {
-        G2A b = G2X::to_affine(ws->gb2);
-        Fq2 x = Fq2::from_mont(b.x), y = Fq2::from_mont(b.y);
-        for (int i = 0; i < NQ; i++) {
-          proof[2 * NQ + i] = x.c0.v[i]; proof[3 * NQ + i] = x.c1.v[i];
-          proof[4 * NQ + i] = y.c0.v[i]; proof[5 * NQ + i] = y.c1.v[i];
-        }
-      } else {
-        G1X cacc = G1X::add_ni(ws->u1, ws->u2);
-        cacc = G1X::add_ni(cacc, G1X::neg(ws->t_rsd));
-        cacc = G1X::add_ni(cacc, ws->sum_l);
-        cacc = G1X::add_ni(cacc, ws->sum_h);
-        G1A cc = G1X::to_affine(cacc);
-        Fq x = Fq::from_mont(cc.x), y = Fq::from_mont(cc.y);
-        for (int i = 0; i < NQ; i++) { proof[6 * NQ + i] = x.v[i]; proof[7 * NQ + i] = y.v[i]; }
-      }
-    });
-    tm.end();
-    d2h(st_, proof_out, proof, 8 * FQB);
-    stream_sync(st_);
-    std::vector<std::pair<const char*, double>> t2;
-    tm.collect(t2);
-    for (auto& e : t2) timings.push_back(e);
+    FixedMults fm = fixed_mults(pk, (const uint32_t*)r, (const uint32_t*)s);
+    finalize_with(pk, fm, partials, world, (const uint32_t*)r, (const uint32_t*)s, proof_out);
+  }
+
+  void prove_full(uint64_t pkh, uint64_t rh, const uint64_t* z, const uint64_t* r, const uint64_t* s,
+                  uint8_t* proof_out) override {
+    Pk& pk = get_pk(pkh);
+    // r*d1, s*d1, rs*d1, s*d2 need nothing from the GPU: run them on a host thread under the kernels
+    auto fut = std::async(std::launch::async, [&pk, r, s] { return fixed_mults(pk, (const uint32_t*)r, (const uint32_t*)s); });
+    std::vector<uint8_t> partial(sizeof(HostPartial));
+    try {
+      prove_partial(pkh, rh, z, partial.data());
+    } catch (...) {
+      fut.wait();
+      throw;
+    }
+    FixedMults fm = fut.get();
+    finalize_with(pk, fm, partial.data(), 1, (const uint32_t*)r, (const uint32_t*)s, proof_out);
   }
 
   // ------------------------------------------------------------------------------ standalone MSM (tests / microbench)
@@ -742,14 +769,16 @@ class Engine : public EngineBase {
   DevBuf<Fr> msm_scalars_;
   MsmPlan plan_misc_;
 
-  template <class F>
+  template <class F, class HF>
   void msm_t(const uint8_t* points, const uint64_t* scalars, uint64_t n, uint8_t* out) {
     typedef Affine<F> A;
     typedef XYZZ<F> X;
+    typedef XYZZ<HF> HX;
+    typedef Affine<HF> HA;
     StageTimer tm(st_);
     msm_pts_.ensure(n * sizeof(A) + 16);
     msm_scalars_.ensure(n + 1);
-    ws_result_.ensure(sizeof(X) + sizeof(A));
+    d_win_.ensure(2 * MAXW * sizeof(X));
     A* pts = (A*)msm_pts_.p;
     h2d(st_, pts, points, n * sizeof(A));
     h2d(st_, msm_scalars_.p, scalars, n * FRB);
@@ -757,30 +786,28 @@ class Engine : public EngineBase {
     tm.begin("msm_plan");
     plan_build(plan_misc_, msm_scalars_.p, n);
     tm.end();
-    X* res = (X*)ws_result_.p;
     tm.begin("msm_exec");
-    msm_exec<F>(plan_misc_, pts, res);
+    msm_exec<F>(plan_misc_, pts, (X*)d_win_.p);
     tm.end();
-    uint32_t* o = (uint32_t*)(ws_result_.p + sizeof(X));
-    launch<k_point_out, 1>(st_, 1, ZKB_LAMBDA(size_t) {
-      A a = X::to_affine(*res);
-      const int words = sizeof(A) / 4;
-      if (a.is_inf()) {
-        for (int i = 0; i < words; i++) o[i] = 0;
-        o[words - 1] = 0x40000000u;
-      } else {
-        A c{F::from_mont(a.x), F::from_mont(a.y)};
-        const uint32_t* raw = (const uint32_t*)&c;
-        for (int i = 0; i < words; i++) o[i] = raw[i];
-      }
-    });
-    d2h(st_, out, o, sizeof(A));
+    std::vector<uint8_t> hw(2 * MAXW * sizeof(X));
+    d2h(st_, hw.data(), d_win_.p, hw.size());
     stream_sync(st_);
     tm.collect(timings);
+    HX res = n ? host_horner<HX>((const HX*)hw.data(), plan_misc_.sh.W, plan_misc_.sh.c) : HX::identity();
+    HA a = HX::to_affine(res);
+    const size_t words = sizeof(A) / 4;
+    uint32_t* o = (uint32_t*)out;
+    if (a.is_inf()) {
+      memset(out, 0, sizeof(A));
+      o[words - 1] = 0x40000000u;
+    } else {
+      HA c{HF::from_mont(a.x), HF::from_mont(a.y)};
+      memcpy(out, &c, sizeof(A));
+    }
   }
   void msm(int group, const uint8_t* points, const uint64_t* scalars, uint64_t n, uint8_t* out) override {
-    if (group == 1) msm_t<Fq>(points, scalars, n, out);
-    else if (group == 2) msm_t<Fq2>(points, scalars, n, out);
+    if (group == 1) msm_t<Fq, HFq>(points, scalars, n, out);
+    else if (group == 2) msm_t<Fq2, HFq2>(points, scalars, n, out);
     else throw Error(ZKB_E_ARG, "group");
   }
 

@@ -19,6 +19,8 @@ struct EngineBase {
   virtual void prove_partial(uint64_t pk, uint64_t r1cs, const uint64_t* z, uint8_t* partial_out) = 0;
   virtual void finalize(uint64_t pk, const uint8_t* partials, uint32_t world, const uint64_t* r, const uint64_t* s,
                         uint8_t* proof_out) = 0;
+  virtual void prove_full(uint64_t pk, uint64_t r1cs, const uint64_t* z, const uint64_t* r, const uint64_t* s,
+                          uint8_t* proof_out) = 0;
   virtual void msm(int group, const uint8_t* points, const uint64_t* scalars, uint64_t n, uint8_t* out) = 0;
   virtual void ntt(uint64_t* data, uint32_t log_n, int inverse, int coset) = 0;
   virtual void witness_map(uint64_t r1cs, const uint64_t* z, uint64_t* h_out, uint64_t cap) = 0;

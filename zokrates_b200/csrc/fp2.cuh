@@ -6,9 +6,10 @@
 
 namespace zkb {
 
-template <class P>
-struct Fp2 {
-  typedef Fp<P> B;
+template <class Bt>
+struct Fp2T {
+  typedef Bt B;
+  typedef Fp2T Fp2;
   B c0, c1;
 
   ZKB_HD static Fp2 zero() { return Fp2{B::zero(), B::zero()}; }
@@ -40,5 +41,8 @@ struct Fp2 {
   ZKB_HD static Fp2 to_mont(const Fp2& a) { return Fp2{B::to_mont(a.c0), B::to_mont(a.c1)}; }
   ZKB_HD static Fp2 from_mont(const Fp2& a) { return Fp2{B::from_mont(a.c0), B::from_mont(a.c1)}; }
 };
+
+template <class P>
+using Fp2 = Fp2T<Fp<P>>;
 
 }  // namespace zkb
