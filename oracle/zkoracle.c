@@ -520,3 +520,133 @@ EXPORT int zko_groth16_prove(int curve, const uint8_t* pk, uint64_t pk_len, uint
   free(aq); free(b1q); free(b2q); free(hq); free(lq); free(zm); free(h); free(hs);
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------- setup
+ * ark-groth16 0.3.0 generate_parameters with an explicit trapdoor:
+ * trapdoor7 = alpha, beta, gamma, delta, tau, g1_k, g2_k (canonical LE), generators g1 = g1_k*G1, g2 = g2_k*G2.
+ * Writes ProvingKey::serialize_unchecked bytes.  Returns 0, or 2 if pk_cap is too small. */
+static void read_fr(const curve_t* c, fe* r, const uint64_t* p) { memset(r, 0, sizeof *r); memcpy(r->l, p, 32); fe_to_mont(&c->fr, r, r); }
+
+static void std_generators(int curve, const curve_t* c, g1_aff* g1, g2_aff* g2) {
+  static const char* BN_G2[4] = {
+    "1800deef121f1e76426a00665e5c4479674322d4f75edadd46debd5cd992f6ed", "198e9393920d483a7260bfb731fb5d25f1aa493335a9e71297e485b7aef312c2",
+    "12c85ea5db8c6deb4aab71808dcb408fe3d1e7690c43d37b4ce6cc0166fa7daa", "090689d0585ff075ec9e99ad690c3395bc4b313370b38ef355acdadcd122975b"};
+  static const char* BLS_G1[2] = {
+    "17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb",
+    "08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1"};
+  static const char* BLS_G2[4] = {
+    "024aa2b2f08f0a91260805272dc51051c6e47ad4fa403b02b4510b647ae3d1770bac0326a805bbefd48056c8c121bdb8",
+    "13e02b6052719f607dacd3a088274f65596bd0d09920b61ab5da61bbdc7f5049334cf11213945d57e5ac7d055d042b7e",
+    "0ce5d527727d6e118cc9cdc6da2e351aadfd9baa8cbdd3a76d429a695160d12c923ac9cc3baca289e193548608b82801",
+    "0606c4a02ea734cc32acd2b02bc28b99cb3e287e85a763af267492ab572e99ab3f370d275cec1da1aaa9075ff05f79be"};
+  const fctx* f = &c->fq;
+  #define HEXFE(dst, str) do { fe t_; memset(&t_, 0, sizeof t_); size_t L_ = strlen(str); for (size_t i_ = 0; i_ < L_; i_++) { char ch = (str)[L_ - 1 - i_]; uint64_t v_ = ch <= '9' ? ch - '0' : ch - 'a' + 10; t_.l[i_ >> 4] |= v_ << (4 * (i_ & 15)); } fe_to_mont(f, &(dst), &t_); } while (0)
+  g1->inf = 0; g2->inf = 0;
+  if (curve == 0) {
+    fe_from_u64(f, &g1->x, 1); fe_from_u64(f, &g1->y, 2);
+    HEXFE(g2->x.c0, BN_G2[0]); HEXFE(g2->x.c1, BN_G2[1]); HEXFE(g2->y.c0, BN_G2[2]); HEXFE(g2->y.c1, BN_G2[3]);
+  } else {
+    HEXFE(g1->x, BLS_G1[0]); HEXFE(g1->y, BLS_G1[1]);
+    HEXFE(g2->x.c0, BLS_G2[0]); HEXFE(g2->x.c1, BLS_G2[1]); HEXFE(g2->y.c0, BLS_G2[2]); HEXFE(g2->y.c1, BLS_G2[3]);
+  }
+}
+
+/* fixed-base multiples with an 8-bit window table (ark uses FixedBaseMSM; the points are the same) */
+static void g1_fixed_base(const curve_t* c, const g1_jac* g, const fe* scalars_mont, uint64_t n, uint8_t* out) {
+  const fctx* fq = &c->fq;
+  g1_aff* table = (g1_aff*)malloc(32 * 256 * sizeof(g1_aff));
+  g1_jac base = *g;
+  for (int j = 0; j < 32; j++) {
+    g1_jac acc; g1_set_inf(fq, &acc);
+    for (int d = 0; d < 256; d++) { g1_to_affine(fq, &table[j * 256 + d], &acc); g1_add(fq, &acc, &acc, &base); }
+    for (int b = 0; b < 8; b++) g1_dbl(fq, &base, &base);
+  }
+#pragma omp parallel for schedule(static)
+  for (uint64_t i = 0; i < n; i++) {
+    fe s; fe_from_mont(&c->fr, &s, &scalars_mont[i]);
+    g1_jac acc; g1_set_inf(fq, &acc);
+    for (int j = 0; j < 32; j++) { unsigned d = (unsigned)(s.l[j >> 3] >> (8 * (j & 7))) & 255u; if (d) g1_add_mixed(fq, &acc, &acc, &table[j * 256 + d]); }
+    g1_aff a; g1_to_affine(fq, &a, &acc); g1_write(c, out + i * 2 * c->fq_bytes, &a);
+  }
+  free(table);
+}
+static void g2_fixed_base(const curve_t* c, const g2_jac* g, const fe* scalars_mont, uint64_t n, uint8_t* out) {
+  const fctx* fq = &c->fq;
+  g2_aff* table = (g2_aff*)malloc(32 * 256 * sizeof(g2_aff));
+  g2_jac base = *g;
+  for (int j = 0; j < 32; j++) {
+    g2_jac acc; g2_set_inf(fq, &acc);
+    for (int d = 0; d < 256; d++) { g2_to_affine(fq, &table[j * 256 + d], &acc); g2_add(fq, &acc, &acc, &base); }
+    for (int b = 0; b < 8; b++) g2_dbl(fq, &base, &base);
+  }
+#pragma omp parallel for schedule(static)
+  for (uint64_t i = 0; i < n; i++) {
+    fe s; fe_from_mont(&c->fr, &s, &scalars_mont[i]);
+    g2_jac acc; g2_set_inf(fq, &acc);
+    for (int j = 0; j < 32; j++) { unsigned d = (unsigned)(s.l[j >> 3] >> (8 * (j & 7))) & 255u; if (d) g2_add_mixed(fq, &acc, &acc, &table[j * 256 + d]); }
+    g2_aff a; g2_to_affine(fq, &a, &acc); g2_write(c, out + i * 4 * c->fq_bytes, &a);
+  }
+  free(table);
+}
+
+EXPORT int zko_groth16_setup(int curve, uint64_t N, uint64_t ni, uint64_t nw, const uint64_t* a_rowptr, const uint32_t* a_col,
+                             const uint64_t* a_val, const uint64_t* b_rowptr, const uint32_t* b_col, const uint64_t* b_val,
+                             const uint64_t* c_rowptr, const uint32_t* c_col, const uint64_t* c_val, const uint64_t* trapdoor7,
+                             uint8_t* pk_out, uint64_t pk_cap, uint64_t* pk_len) {
+  curves_init();
+  const curve_t* c = &CURVES[curve];
+  const fctx* f = &c->fr;
+  const int g1b = 2 * c->fq_bytes, g2b = 4 * c->fq_bytes;
+  uint64_t m = ni + nw, dom = N + ni; size_t n = 1; int lg = 0;
+  while (n < dom) { n <<= 1; lg++; }
+  uint64_t total = g1b + 3 * g2b + 8 + ni * g1b + 2 * g1b + 2 * (8 + m * g1b) + 8 + m * g2b + 8 + (n - 1) * g1b + 8 + (m - ni) * g1b;
+  *pk_len = total;
+  if (pk_cap < total) return 2;
+  fe alpha, beta, gamma, delta, tau; uint64_t gk[2][4];
+  read_fr(c, &alpha, trapdoor7); read_fr(c, &beta, trapdoor7 + 4); read_fr(c, &gamma, trapdoor7 + 8);
+  read_fr(c, &delta, trapdoor7 + 12); read_fr(c, &tau, trapdoor7 + 16);
+  memcpy(gk[0], trapdoor7 + 20, 32); memcpy(gk[1], trapdoor7 + 24, 32);
+  /* u = ifft(tau^k) = Lagrange coefficients at tau */
+  fe* pw = (fe*)malloc(n * sizeof(fe)); fe* u = (fe*)malloc(n * sizeof(fe));
+  pw[0] = f->r1; for (size_t i = 1; i < n; i++) fe_mul(f, &pw[i], &pw[i - 1], &tau);
+  memcpy(u, pw, n * sizeof(fe));
+  fr_transform(c, u, lg, 1, 0);
+  fe* abc[3];
+  const uint64_t* rp[3] = {a_rowptr, b_rowptr, c_rowptr}; const uint32_t* cl[3] = {a_col, b_col, c_col}; const uint64_t* vl[3] = {a_val, b_val, c_val};
+  for (int k = 0; k < 3; k++) {
+    abc[k] = (fe*)calloc(m ? m : 1, sizeof(fe));
+    if (k == 0) for (uint64_t i = 0; i < ni; i++) abc[0][i] = u[N + i];
+    for (uint64_t row = 0; row < N; row++)
+      for (uint64_t e = rp[k][row]; e < rp[k][row + 1]; e++) {
+        fe v, t; read_fr(c, &v, vl[k] + 4 * e); fe_mul(f, &t, &v, &u[row]); fe_add(f, &abc[k][cl[k][e]], &abc[k][cl[k][e]], &t);
+      }
+  }
+  fe ginv, dinv, zt, hs; fe_inv(f, &ginv, &gamma); fe_inv(f, &dinv, &delta);
+  zt = tau; for (int i = 0; i < lg; i++) fe_sqr(f, &zt, &zt);
+  fe_sub(f, &zt, &zt, &f->r1); fe_mul(f, &hs, &zt, &dinv);
+  fe* lq = (fe*)malloc((m ? m : 1) * sizeof(fe)); fe* hq = (fe*)malloc(n * sizeof(fe));
+  for (uint64_t i = 0; i < m; i++) {
+    fe t1, t2; fe_mul(f, &t1, &beta, &abc[0][i]); fe_mul(f, &t2, &alpha, &abc[1][i]); fe_add(f, &t1, &t1, &t2); fe_add(f, &t1, &t1, &abc[2][i]);
+    fe_mul(f, &lq[i], &t1, i < ni ? &ginv : &dinv);
+  }
+  for (size_t i = 0; i < n; i++) fe_mul(f, &hq[i], &pw[i], &hs);
+  g1_aff s1; g2_aff s2; std_generators(curve, c, &s1, &s2);
+  g1_jac j1, g1; g2_jac j2, g2;
+  g1_from_affine(&c->fq, &j1, &s1); g2_from_affine(&c->fq, &j2, &s2);
+  g1_mul(&c->fq, &g1, &j1, gk[0], 4); g2_mul(&c->fq, &g2, &j2, gk[1], 4);
+  uint8_t* o = pk_out; uint64_t len;
+  g1_fixed_base(c, &g1, &alpha, 1, o); o += g1b;
+  g2_fixed_base(c, &g2, &beta, 1, o); o += g2b;
+  g2_fixed_base(c, &g2, &gamma, 1, o); o += g2b;
+  g2_fixed_base(c, &g2, &delta, 1, o); o += g2b;
+  len = ni; memcpy(o, &len, 8); o += 8; g1_fixed_base(c, &g1, lq, ni, o); o += ni * g1b;
+  g1_fixed_base(c, &g1, &beta, 1, o); o += g1b;
+  g1_fixed_base(c, &g1, &delta, 1, o); o += g1b;
+  len = m; memcpy(o, &len, 8); o += 8; g1_fixed_base(c, &g1, abc[0], m, o); o += m * g1b;
+  memcpy(o, &len, 8); o += 8; g1_fixed_base(c, &g1, abc[1], m, o); o += m * g1b;
+  memcpy(o, &len, 8); o += 8; g2_fixed_base(c, &g2, abc[1], m, o); o += m * g2b;
+  len = n - 1; memcpy(o, &len, 8); o += 8; g1_fixed_base(c, &g1, hq, n - 1, o); o += (n - 1) * g1b;
+  len = m - ni; memcpy(o, &len, 8); o += 8; g1_fixed_base(c, &g1, lq + ni, m - ni, o); o += (m - ni) * g1b;
+  free(pw); free(u); free(abc[0]); free(abc[1]); free(abc[2]); free(lq); free(hq);
+  return (uint64_t)(o - pk_out) == total ? 0 : 6;
+}

@@ -69,3 +69,20 @@ class OracleC:
         if rc != 0:
             raise RuntimeError(f"zko_groth16_prove rc={rc}")
         return out.tobytes(), times
+
+    def setup(self, curve, r1cs, trapdoor7):
+        from zokrates_b200._lib import fr_array
+        td = fr_array(trapdoor7)
+        args, keep = self._mats(r1cs)
+        n = C.c_uint64()
+        cap = 1 << 16
+        while True:
+            out = np.zeros(cap, dtype=np.uint8)
+            rc = self.dll.zko_groth16_setup(curve, C.c_uint64(r1cs.num_constraints), C.c_uint64(r1cs.num_instance),
+                                            C.c_uint64(r1cs.num_witness), *args, C.c_void_p(td.ctypes.data),
+                                            C.c_void_p(out.ctypes.data), C.c_uint64(cap), C.byref(n))
+            if rc == 0:
+                return out[:n.value].tobytes()
+            if rc != 2:
+                raise RuntimeError(f"zko_groth16_setup rc={rc}")
+            cap = int(n.value)

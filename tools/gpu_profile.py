@@ -13,7 +13,7 @@ res = {}
 for lg in sizes:
     for dist in ("uniform", "bits"):
         t = time.time()
-        r1cs, z = synthetic.make("bn128", (1 << lg) - 2, distribution=dist)
+        r1cs, z = synthetic.make_layered(ctx, "bn128", (1 << lg) - 2, distribution=dist)
         tgen = time.time() - t
         h = ctx.r1cs_load(r1cs.num_constraints, r1cs.num_instance, r1cs.num_witness, r1cs.matrices())
         t = time.time()

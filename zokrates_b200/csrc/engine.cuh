@@ -33,6 +33,7 @@ struct StageTimer {
 #if !defined(ZKB_EMU)
   struct Ev { const char* name; cudaEvent_t a, b; };
   std::vector<Ev> evs;
+  std::vector<size_t> open;  // stack of stages begun but not ended (stages may nest)
   Stream st;
   explicit StageTimer(Stream s) : st(s) {}
   void begin(const char* name) {
@@ -40,9 +41,14 @@ struct StageTimer {
     ZKB_CUDA(cudaEventCreate(&e.a));
     ZKB_CUDA(cudaEventCreate(&e.b));
     ZKB_CUDA(cudaEventRecord(e.a, st.s));
+    open.push_back(evs.size());
     evs.push_back(e);
   }
-  void end() { ZKB_CUDA(cudaEventRecord(evs.back().b, st.s)); }
+  void end() {
+    size_t i = open.back();
+    open.pop_back();
+    ZKB_CUDA(cudaEventRecord(evs[i].b, st.s));
+  }
   void collect(std::vector<std::pair<const char*, double>>& out) {
     out.clear();
     for (auto& e : evs) {
@@ -450,7 +456,8 @@ class Engine : public EngineBase {
   }
 
   template <class F>
-  void msm_exec(const MsmPlan& pl, const Affine<F>* pts, XYZZ<F>* win_out /* 2 W entries */) {
+  void msm_exec(const MsmPlan& pl, const Affine<F>* pts, XYZZ<F>* win_out /* 2 W entries */, StageTimer* tm = nullptr,
+                const char* accum_name = nullptr) {
     typedef XYZZ<F> X;
     if (pl.sh.n == 0) return;
     const uint32_t NB = pl.nbuckets, W = pl.sh.W, B = pl.sh.B, c = pl.sh.c;
@@ -461,7 +468,9 @@ class Engine : public EngineBase {
     for (int k = 0; k < 2; k++) { ws_key_[k].ensure(2 * (size_t)nt1 + 2); ws_val_[k].ensure((2 * (size_t)nt1 + 2) * sizeof(X)); }
     const uint32_t* of = pl.offsets.p; const uint32_t* so = pl.sorted.p;
     uint32_t* k0 = ws_key_[0].p; X* v0 = (X*)ws_val_[0].p;
+    if (tm && accum_name) tm->begin(accum_name);
     launch<k_msm_accum1>(st_, nt1, ZKB_LAMBDA(size_t t) { msm_accum1_body<F>(NB, T1, of, so, pts, buckets, k0, v0, nt1, (uint32_t)t); });
+    if (tm && accum_name) tm->end();
     uint32_t L = 2 * nt1;
     int cur = 0;
     while (true) {
@@ -664,22 +673,22 @@ class Engine : public EngineBase {
     plan_build(plan_h_, r.h.p + pk.hlo, pk.hhi - pk.hlo);
     tm.end();
     tm.begin("msm_h");
-    msm_exec<Fq>(plan_h_, pk.h.p, w_h);
+    msm_exec<Fq>(plan_h_, pk.h.p, w_h, &tm, "accum1_g1_h");
     tm.end();
     tm.begin("msm_plan_z");
     plan_build(plan_z_, r.z_canon.p + 1 + pk.lo, pk.hi - pk.lo);
     tm.end();
     tm.begin("msm_l");
-    msm_exec<Fq>(plan_z_, pk.l.p, w_l);
+    msm_exec<Fq>(plan_z_, pk.l.p, w_l, &tm, "accum1_g1_l");
     tm.end();
     tm.begin("msm_a");
-    msm_exec<Fq>(plan_z_, pk.a.p, w_a);
+    msm_exec<Fq>(plan_z_, pk.a.p, w_a, &tm, "accum1_g1_a");
     tm.end();
     tm.begin("msm_b1");
-    msm_exec<Fq>(plan_z_, pk.b1.p, w_b1);
+    msm_exec<Fq>(plan_z_, pk.b1.p, w_b1, &tm, "accum1_g1_b1");
     tm.end();
     tm.begin("msm_b2");
-    msm_exec<Fq2>(plan_z_, pk.b2.p, w_b2);
+    msm_exec<Fq2>(plan_z_, pk.b2.p, w_b2, &tm, "accum1_g2_b2");
     tm.end();
     std::vector<uint8_t> hw(4 * slot1 + slot2);
     tm.begin("d2h_windows");
@@ -787,7 +796,7 @@ class Engine : public EngineBase {
     plan_build(plan_misc_, msm_scalars_.p, n);
     tm.end();
     tm.begin("msm_exec");
-    msm_exec<F>(plan_misc_, pts, (X*)d_win_.p);
+    msm_exec<F>(plan_misc_, pts, (X*)d_win_.p, &tm, "accum1");
     tm.end();
     std::vector<uint8_t> hw(2 * MAXW * sizeof(X));
     d2h(st_, hw.data(), d_win_.p, hw.size());
