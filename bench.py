@@ -170,7 +170,6 @@ def main():
     pk = ctx.setup(r1cs_h, TRAPDOOR)
     setup_ms = ctx.timings()
     pk_h = ctx.pk_load(pk, rank, world)
-    pk_full_h = ctx.pk_load(pk, 0, 1) if world > 1 and rank == 0 else pk_h
     pk_bytes = len(pk)
     del pk
     z_pinned = torch.from_numpy(z).pin_memory()
@@ -184,12 +183,9 @@ def main():
         """5 partial sums per rank -> all ranks (NCCL all_gather of a few hundred bytes) -> rank 0 finishes."""
         if world == 1:
             return ctx.finalize(pk_h, partial, 1, *r_s)
-        mine = torch.from_numpy(partial).cuda()
-        allp = torch.empty(world * partial_bytes, dtype=torch.uint8, device="cuda")
-        dist.all_gather_into_tensor(allp, mine)
-        if rank == 0:
-            return ctx.finalize(pk_full_h, allp.cpu().numpy(), world, *r_s)
-        return None
+        from zokrates_b200.distributed import gather_partials
+        allp = gather_partials(partial, device=torch.device("cuda", local))
+        return ctx.finalize(pk_h, allp, world, *r_s) if rank == 0 else None
 
     def step_resident():
         if world == 1:

@@ -1,0 +1,49 @@
+"""N > 1 path on CPU: world_size-2/3 gloo process groups drive the sharded prover (host-emulation engine);
+the gathered proof must equal the single-rank proof byte for byte."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, emu_path, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from zokrates_b200 import backend, distributed, synthetic
+        from zokrates_b200._lib import Library
+        lib = Library(emu_path)
+        r1cs, z = synthetic.make("bn128", 60, seed=3)
+        ctx0 = backend.context("bn128", 0, lib)
+        h = ctx0.r1cs_load(r1cs.num_constraints, r1cs.num_instance, r1cs.num_witness, r1cs.matrices())
+        pk = ctx0.setup(h, [3, 5, 7, 11, 13, 17, 19])
+        sess = backend.ProverSession("bn128", r1cs, pk, 0, rank, world, lib=lib)
+        proof = distributed.prove_sharded(sess, z, 111, 222)
+        if rank == 0:
+            single = backend.ProverSession("bn128", r1cs, pk, 0, 0, 1, lib=lib).prove_raw(z, 111, 222)
+            np.save(out_path, np.array([proof == single, len(proof)]))
+        else:
+            assert proof is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_prove_gloo(world, emu_lib, tmp_path):
+    out = str(tmp_path / "res.npy")
+    mp.spawn(_worker, args=(world, _free_port(), emu_lib.path, out), nprocs=world, join=True)
+    ok, n = np.load(out)
+    assert ok == 1 and n == 256

@@ -112,29 +112,29 @@ ZKB_HDN inline void msm_accum1_body(uint32_t nbuckets, uint32_t T, const uint32_
     }
     uint32_t b = lo;
     const uint32_t cstart = pos;
-    while (pos < end) {
-      while (offsets[b + 1] <= pos) b++;  // skip empty buckets
-      uint32_t bstart = offsets[b], bend = offsets[b + 1];
-      uint32_t seg_end = bend < end ? bend : end;
-      XYZZ<F> acc = XYZZ<F>::identity();
-      for (uint32_t p = pos; p < seg_end; p++) {
-        uint32_t e = sorted[p];
-        Affine<F> q = points[e & ~MSM_NEG];
-        if (e & MSM_NEG) q.y = F::neg(q.y);
-        acc = XYZZ<F>::madd(acc, q);
+    while (offsets[b + 1] <= pos) b++;  // (lo may be an empty bucket sharing the offset)
+    uint32_t bstart = offsets[b], bend = offsets[b + 1];
+    XYZZ<F> acc = XYZZ<F>::identity();
+    // ONE flat loop over the chunk: the bucket change is a short predicated block, so every lane of the
+    // warp meets at the same mixed addition each iteration (no nested-loop divergence).
+    for (uint32_t p = pos; p < end; p++) {
+      if (p == bend) {
+        if (bstart >= cstart) buckets[b] = acc;            // complete (it also ends inside the chunk)
+        else { k0 = b; pval[2 * (size_t)t] = acc; }        // began in the previous chunk
+        b++;
+        while (offsets[b + 1] <= p) b++;
+        bstart = p;
+        bend = offsets[b + 1];
+        acc = XYZZ<F>::identity();
       }
-      bool complete = bstart >= cstart && bend <= end;
-      if (complete) {
-        buckets[b] = acc;
-      } else if (bstart < cstart) {  // continues from the previous chunk: first segment
-        k0 = b;
-        pval[2 * (size_t)t] = acc;
-      } else {                       // runs into the next chunk: last segment
-        k1 = b;
-        pval[2 * (size_t)t + 1] = acc;
-      }
-      pos = seg_end;
+      uint32_t e = sorted[p];
+      Affine<F> q = points[e & ~MSM_NEG];
+      if (e & MSM_NEG) q.y = F::neg(q.y);
+      acc = XYZZ<F>::madd(acc, q);
     }
+    if (bstart >= cstart && bend <= end) buckets[b] = acc;
+    else if (bstart < cstart) { k0 = b; pval[2 * (size_t)t] = acc; }
+    else { k1 = b; pval[2 * (size_t)t + 1] = acc; }
   }
   pkey[2 * (size_t)t] = k0;
   pkey[2 * (size_t)t + 1] = k1;
@@ -190,7 +190,7 @@ ZKB_HDN inline void msm_accum2_body(uint32_t L, uint32_t T, const uint32_t* key,
       cur = k;
       acc = XYZZ<F>::identity();
     }
-    if (p < e) acc = XYZZ<F>::add_ni(acc, val[p]);
+    if (p < e) acc = XYZZ<F>::add(acc, val[p]);
   }
   okey[2 * (size_t)t] = k0;
   okey[2 * (size_t)t + 1] = k1;
@@ -211,13 +211,13 @@ ZKB_HDN inline void msm_tree_body(uint32_t W, uint32_t cnt_in, uint32_t lr, uint
   uint32_t hi = lo + Lr < cnt_in ? lo + Lr : cnt_in;
   XYZZ<F> run = XYZZ<F>::identity(), wrel = XYZZ<F>::identity(), wsum = XYZZ<F>::identity();
   for (uint32_t i = hi; i-- > lo;) {
-    run = XYZZ<F>::add_ni(run, A[i]);
-    if (i > lo) wrel = XYZZ<F>::add_ni(wrel, run);
-    if (lvl > 0) wsum = XYZZ<F>::add_ni(wsum, inWt[(size_t)w * cnt_in + i]);
+    run = XYZZ<F>::add(run, A[i]);
+    if (i > lo) wrel = XYZZ<F>::add(wrel, run);
+    if (lvl > 0) wsum = XYZZ<F>::add(wsum, inWt[(size_t)w * cnt_in + i]);
   }
   for (uint32_t d = 0; d < lr * lvl; d++) wrel = XYZZ<F>::dbl_ni(wrel);  // times S = 2^(lr*lvl)
   outA[(size_t)w * cnt_out + k] = run;
-  outWt[(size_t)w * cnt_out + k] = XYZZ<F>::add_ni(wsum, wrel);
+  outWt[(size_t)w * cnt_out + k] = XYZZ<F>::add(wsum, wrel);
 }
 
 // ---- window combine: result = sum_w 2^(c w) (Wt_w + A_w)  (single thread) ------------------------
@@ -226,7 +226,7 @@ ZKB_HDN inline void msm_horner_body(uint32_t W, uint32_t c, const XYZZ<F>* A, co
   XYZZ<F> acc = XYZZ<F>::identity();
   for (uint32_t w = W; w-- > 0;) {
     for (uint32_t d = 0; d < c; d++) acc = XYZZ<F>::dbl_ni(acc);
-    acc = XYZZ<F>::add_ni(acc, XYZZ<F>::add_ni(A[w], Wt[w]));
+    acc = XYZZ<F>::add(acc, XYZZ<F>::add(A[w], Wt[w]));
   }
   *out = acc;
 }
