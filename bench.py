@@ -252,19 +252,21 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-    n_pairs = (r1cs.num_variables - 1) // world          # (scalar, point) pairs one accum1 launch of msm_a processes
-    acc_ms = stage_res.get("accum1_g1_a", 0.0)
+    # roofline kernel: the bucket accumulation of the h_query MSM (no infinity points, uniform scalars, so the
+    # canonical n*W*10 count is not flattered by the infinity-skipping views used for a/b1/b2)
+    n_pairs = (r1cs.domain_size - 1) // world            # (scalar, point) pairs one accum1 launch of msm_h processes
+    acc_ms = stage_res.get("accum1_g1_h", 0.0)
     roofline = roofline_mm = None
     if rank == 0 and acc_ms > 0:
         modmul_peak = ctx.peak_probe(1, 4000)
         imad_peak = ctx.peak_probe(0, 40000)
         alg_bytes = n_pairs * 96.0                       # 32 B scalar + 64 B affine point per pair
         alg_muls = n_pairs * 16 * 10.0                   # canonical: W = 16 windows x 10 Fq-mul per mixed add
-        roofline = {"kernel": "msm_accum1<Fq> (a_query)", "bound": "hbm", "achieved": alg_bytes / (acc_ms * 1e-3) / 1e9,
+        roofline = {"kernel": "k_msm_accum1<Fq> (h_query MSM)", "bound": "hbm", "achieved": alg_bytes / (acc_ms * 1e-3) / 1e9,
                     "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / (acc_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
                     "peak_source": hbm_src, "avg_launch_ms": acc_ms,
                     "note": "the kernel is integer-multiply bound, not HBM bound (230 MAD/B): see roofline_modmul"}
-        roofline_mm = {"kernel": "msm_accum1<Fq> (a_query)", "bound": "int32-mad", "achieved": alg_muls / (acc_ms * 1e-3),
+        roofline_mm = {"kernel": "k_msm_accum1<Fq> (h_query MSM)", "bound": "int32-mad", "achieved": alg_muls / (acc_ms * 1e-3),
                        "peak": modmul_peak, "unit": "Fq-mul/s", "frac": alg_muls / (acc_ms * 1e-3) / modmul_peak,
                        "imad_wide_peak_per_s": imad_peak, "mads_per_mul": 136,
                        "peak_source": "in-repo probe: register-resident Montgomery multiplications (zkb_peak_probe kind 1)"}

@@ -96,12 +96,61 @@ static __global__ void zkb_scan_kernel(const uint32_t* counts, uint32_t* offsets
   if (tid == 1023) offsets[n] = sums[1023];
 }
 #endif
-inline void exclusive_scan(Stream st, const uint32_t* counts, uint32_t* offsets, uint32_t n) {
 #if !defined(ZKB_EMU)
+// three-phase scan for large n: per-tile sums, scan of the tile sums (single block), per-tile rescan
+static constexpr int SCAN_BLOCK = 256, SCAN_PER = 8, SCAN_TILE = SCAN_BLOCK * SCAN_PER;
+static __global__ void zkb_scan_tile_sums(const uint32_t* in, uint32_t* tile_sums, uint32_t n) {
+  __shared__ uint32_t red[SCAN_BLOCK / 32];
+  const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_PER; k++) s += (base + k < n) ? in[base + k] : 0;
+  for (int off = 16; off; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int k = 0; k < SCAN_BLOCK / 32; k++) t += red[k];
+    tile_sums[blockIdx.x] = t;
+  }
+}
+static __global__ void zkb_scan_tile_apply(const uint32_t* in, const uint32_t* tile_offsets, uint32_t* out, uint32_t n,
+                                           uint32_t ntiles) {
+  __shared__ uint32_t wsum[SCAN_BLOCK / 32];
+  const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER;
+  uint32_t v[SCAN_PER], s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_PER; k++) { v[k] = (base + k < n) ? in[base + k] : 0; s += v[k]; }
+  // exclusive scan of the per-thread sums across the block
+  uint32_t incl = s;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int off = 1; off < 32; off <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= (uint32_t)off) incl += y; }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  uint32_t wbase = 0;
+  for (uint32_t k = 0; k < warp; k++) wbase += wsum[k];
+  uint32_t run = tile_offsets[blockIdx.x] + wbase + incl - s;
+#pragma unroll
+  for (int k = 0; k < SCAN_PER; k++) { if (base + k < n) out[base + k] = run; run += v[k]; }
+  if (blockIdx.x == ntiles - 1 && threadIdx.x == SCAN_BLOCK - 1) out[n] = tile_offsets[ntiles];
+}
+#endif
+inline void exclusive_scan(Stream st, const uint32_t* counts, uint32_t* offsets, uint32_t n, uint32_t* tile_tmp = nullptr) {
+#if !defined(ZKB_EMU)
+  if (tile_tmp && n > 4096) {
+    const uint32_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    launch_counter() += 3;
+    zkb_scan_tile_sums<<<ntiles, SCAN_BLOCK, 0, st.s>>>(counts, tile_tmp, n);
+    zkb_scan_kernel<<<1, 1024, 0, st.s>>>(tile_tmp, tile_tmp + ntiles + 1, ntiles);   // offsets of the tiles (+ total)
+    zkb_scan_tile_apply<<<ntiles, SCAN_BLOCK, 0, st.s>>>(counts, tile_tmp + ntiles + 1, offsets, n, ntiles);
+    ZKB_CUDA(cudaGetLastError());
+    return;
+  }
   launch_counter()++;
   zkb_scan_kernel<<<1, 1024, 0, st.s>>>(counts, offsets, n);
   ZKB_CUDA(cudaGetLastError());
 #else
+  (void)tile_tmp;
   uint32_t base = 0;
   for (uint32_t i = 0; i < n; i++) { offsets[i] = base; base += counts[i]; }
   offsets[n] = base;
@@ -114,7 +163,8 @@ struct MsmPlan {
   uint32_t nbuckets = 0;
   uint32_t T1 = 32, T2 = 32;
   uint32_t nt1 = 0;  // level-1 chunks
-  DevBuf<uint32_t> digits, counts, offsets, cursor, sorted;
+  uint32_t nviews = 1;
+  DevBuf<uint32_t> digits, counts, offsets, cursor, sorted, scan_tmp;
 };
 
 inline uint32_t msm_pick_c(uint64_t n, int fr_bits) {
@@ -420,11 +470,10 @@ class Engine : public EngineBase {
   }
 
   // ------------------------------------------------------------------------------ MSM
-  DevBuf<uint8_t> ws_buckets_, ws_val_[2], ws_tree_[4];
-  DevBuf<uint32_t> ws_key_[2];
 
-  void plan_build(MsmPlan& pl, const Fr* scalars, uint64_t n) {
+  void plan_build(MsmPlan& pl, const Fr* scalars, uint64_t n, uint32_t nviews = 1, const uint8_t* skip = nullptr) {
     pl.sh.n = (uint32_t)n;
+    pl.nviews = nviews;
     if (n == 0) return;
     uint32_t c = msm_pick_c(n, C::FR_BITS);
     pl.sh.c = c;
@@ -432,7 +481,7 @@ class Engine : public EngineBase {
     pl.sh.B = 1u << (c - 1);
     pl.nbuckets = pl.sh.W * pl.sh.B;
     uint64_t total = n * pl.sh.W;
-    if (total >= (1ull << 32)) throw Error(ZKB_E_ARG, "msm too large");
+    if (total * nviews >= (1ull << 32)) throw Error(ZKB_E_ARG, "msm too large");
     // chunk size: aim for several waves of resident threads, at least 8 entries per chunk
     uint64_t target = 600000;
     uint64_t T = (total + target - 1) / target;
@@ -442,66 +491,109 @@ class Engine : public EngineBase {
     pl.T1 = (uint32_t)T;
     pl.T2 = 32;
     pl.nt1 = (uint32_t)((total + pl.T1 - 1) / pl.T1);
-    pl.digits.ensure(total); pl.sorted.ensure(total);
-    pl.counts.ensure(pl.nbuckets); pl.cursor.ensure(pl.nbuckets); pl.offsets.ensure(pl.nbuckets + 1);
-    dev_zero(st_, pl.counts.p, (size_t)pl.nbuckets * 4);
-    dev_zero(st_, pl.cursor.p, (size_t)pl.nbuckets * 4);
+    const uint32_t NB = pl.nbuckets;
+    pl.digits.ensure(total); pl.sorted.ensure(total * nviews);
+    pl.counts.ensure((size_t)NB * nviews); pl.cursor.ensure((size_t)NB * nviews); pl.offsets.ensure((size_t)(NB + 1) * nviews);
+    dev_zero(st_, pl.counts.p, (size_t)NB * nviews * 4);
+    dev_zero(st_, pl.cursor.p, (size_t)NB * nviews * 4);
     MsmShape sh = pl.sh;
     const uint32_t* sc = (const uint32_t*)scalars;
     uint32_t* dg = pl.digits.p; uint32_t* cn = pl.counts.p; uint32_t* of = pl.offsets.p; uint32_t* cu = pl.cursor.p;
     uint32_t* so = pl.sorted.p;
-    launch<k_msm_digits>(st_, n, ZKB_LAMBDA(size_t t) { msm_digits_body(sh, sc, dg, cn, (uint32_t)t); });
-    exclusive_scan(st_, cn, of, pl.nbuckets);
-    launch<k_msm_scatter>(st_, total, ZKB_LAMBDA(size_t t) { msm_scatter_body(sh, dg, of, cu, so, t); });
+    launch<k_msm_digits>(st_, n, ZKB_LAMBDA(size_t t) { msm_digits_body(sh, nviews, skip, sc, dg, cn, (uint32_t)t); });
+    pl.scan_tmp.ensure(2 * (NB / 2048 + 4));
+    for (uint32_t v = 0; v < nviews; v++) exclusive_scan(st_, cn + (size_t)v * NB, of + (size_t)v * (NB + 1), NB, pl.scan_tmp.p);
+    launch<k_msm_scatter>(st_, total, ZKB_LAMBDA(size_t t) { msm_scatter_body(sh, nviews, skip, dg, of, cu, so, t); });
   }
 
+  // per-MSM scratch so that the latency-bound tails of different MSMs can overlap
+  struct MsmWs {
+    DevBuf<uint8_t> buckets, val[2], tree[4];
+    DevBuf<uint32_t> key[2];
+    Stream tail;          // high-priority side stream for accum2 / tree
+    Event acc_done, tail_done;
+    bool has_stream = false;
+  };
+  static constexpr int NUM_WS = 6;   // h, l, a, b1, b2, misc
+  MsmWs ws_[NUM_WS];
+  Stream tail_stream(MsmWs& ws) {
+    if (!ws.has_stream) { ws.tail = stream_create_high_priority(); ws.has_stream = true; }
+    return ws.tail;
+  }
+  ~Engine() override {
+    for (auto& w : ws_) { if (w.has_stream) stream_destroy(w.tail); w.acc_done.destroy(); w.tail_done.destroy(); }
+  }
+
+  // phase 1 (main stream): bucket accumulation of one MSM.  Throughput-bound (INT32 multiply pipe).
   template <class F>
-  void msm_exec(const MsmPlan& pl, const Affine<F>* pts, XYZZ<F>* win_out /* 2 W entries */, StageTimer* tm = nullptr,
-                const char* accum_name = nullptr) {
+  void msm_accumulate(const MsmPlan& pl, const Affine<F>* pts, MsmWs& ws, StageTimer* tm, const char* accum_name, uint32_t view) {
     typedef XYZZ<F> X;
     if (pl.sh.n == 0) return;
-    const uint32_t NB = pl.nbuckets, W = pl.sh.W, B = pl.sh.B, c = pl.sh.c;
-    ws_buckets_.ensure((size_t)NB * sizeof(X));
-    X* buckets = (X*)ws_buckets_.p;
+    const uint32_t NB = pl.nbuckets;
+    ws.buckets.ensure((size_t)NB * sizeof(X));
+    X* buckets = (X*)ws.buckets.p;
+    const uint32_t nt1 = pl.nt1, T1 = pl.T1;
+    for (int k = 0; k < 2; k++) { ws.key[k].ensure(2 * (size_t)nt1 + 2); ws.val[k].ensure((2 * (size_t)nt1 + 2) * sizeof(X)); }
+    ws.tail_done.wait(st_);  // the previous proof's tail may still be reading these buffers
     dev_zero(st_, buckets, (size_t)NB * sizeof(X));
-    const uint32_t nt1 = pl.nt1, T1 = pl.T1, T2 = pl.T2;
-    for (int k = 0; k < 2; k++) { ws_key_[k].ensure(2 * (size_t)nt1 + 2); ws_val_[k].ensure((2 * (size_t)nt1 + 2) * sizeof(X)); }
-    const uint32_t* of = pl.offsets.p; const uint32_t* so = pl.sorted.p;
-    uint32_t* k0 = ws_key_[0].p; X* v0 = (X*)ws_val_[0].p;
+    const uint32_t* of = pl.offsets.p + (size_t)view * (NB + 1);
+    const uint32_t* so = pl.sorted.p + (size_t)view * pl.sh.n * pl.sh.W;
+    uint32_t* k0 = ws.key[0].p; X* v0 = (X*)ws.val[0].p;
     if (tm && accum_name) tm->begin(accum_name);
     launch<k_msm_accum1>(st_, nt1, ZKB_LAMBDA(size_t t) { msm_accum1_body<F>(NB, T1, of, so, pts, buckets, k0, v0, nt1, (uint32_t)t); });
     if (tm && accum_name) tm->end();
+    ws.acc_done.record(st_);
+  }
+
+  // phase 2 (side stream): reduce chunk-boundary partials, then the per-window bucket tree.  Latency-bound:
+  // a few thousand threads doing ~20 dependent point additions per level, so it runs on a high-priority
+  // stream underneath the next MSM's accumulation.
+  template <class F>
+  void msm_tail(const MsmPlan& pl, MsmWs& ws, XYZZ<F>* win_out /* 2 W entries */) {
+    typedef XYZZ<F> X;
+    if (pl.sh.n == 0) return;
+    Stream ts = tail_stream(ws);
+    ws.acc_done.wait(ts);
+    const uint32_t W = pl.sh.W, B = pl.sh.B, T2 = pl.T2, nt1 = pl.nt1;
+    X* buckets = (X*)ws.buckets.p;
     uint32_t L = 2 * nt1;
     int cur = 0;
     while (true) {
       uint32_t nt = L / T2 + 1;
-      const uint32_t* ik = ws_key_[cur].p; const X* iv = (const X*)ws_val_[cur].p;
-      uint32_t* ok = ws_key_[cur ^ 1].p; X* ov = (X*)ws_val_[cur ^ 1].p;
+      const uint32_t* ik = ws.key[cur].p; const X* iv = (const X*)ws.val[cur].p;
+      uint32_t* ok = ws.key[cur ^ 1].p; X* ov = (X*)ws.val[cur ^ 1].p;
       uint32_t Lc = L;
-      launch<k_msm_accum2>(st_, nt, ZKB_LAMBDA(size_t t) { msm_accum2_body<F>(Lc, T2, ik, iv, buckets, ok, ov, nt, (uint32_t)t); });
+      launch<k_msm_accum2>(ts, nt, ZKB_LAMBDA(size_t t) { msm_accum2_body<F>(Lc, T2, ik, iv, buckets, ok, ov, nt, (uint32_t)t); });
       if (nt == 1) break;
       L = 2 * nt;
       cur ^= 1;
     }
-    // bucket tree (fan-in 8) then Horner over the windows
     const uint32_t lr = 3;
     size_t first = (size_t)W * ((B + 7) / 8);
-    for (int k = 0; k < 4; k++) ws_tree_[k].ensure(first * sizeof(X));
+    for (int k = 0; k < 4; k++) ws.tree[k].ensure(first * sizeof(X));
     const X* inA = buckets; const X* inWt = nullptr;
     uint32_t cnt = B, lvl = 0;
     int pp = 0;
     while (cnt > 1) {
       uint32_t cnt_out = (cnt + 7) / 8;
-      X* oA = (X*)ws_tree_[pp].p; X* oW = (X*)ws_tree_[pp + 1].p;
+      X* oA = (X*)ws.tree[pp].p; X* oW = (X*)ws.tree[pp + 1].p;
       const X* iA = inA; const X* iW = inWt;
       uint32_t ci = cnt, lv = lvl;
-      launch<k_msm_tree>(st_, (size_t)W * cnt_out, ZKB_LAMBDA(size_t t) { msm_tree_body<F>(W, ci, lr, lv, iA, iW, oA, oW, (uint32_t)t); });
+      launch<k_msm_tree>(ts, (size_t)W * cnt_out, ZKB_LAMBDA(size_t t) { msm_tree_body<F>(W, ci, lr, lv, iA, iW, oA, oW, (uint32_t)t); });
       inA = oA; inWt = oW; cnt = cnt_out; lvl++;
       pp ^= 2;
     }
     // window sums (A_w, Wt_w) -> caller's slot; the 2^(c w) Horner runs on the host (see fp64.cuh)
-    d2d(st_, win_out, inA, (size_t)W * sizeof(X));
-    d2d(st_, win_out + W, inWt, (size_t)W * sizeof(X));
+    d2d(ts, win_out, inA, (size_t)W * sizeof(X));
+    d2d(ts, win_out + W, inWt, (size_t)W * sizeof(X));
+    ws.tail_done.record(ts);
+  }
+
+  template <class F>
+  void msm_exec(const MsmPlan& pl, const Affine<F>* pts, XYZZ<F>* win_out, MsmWs& ws, StageTimer* tm = nullptr,
+                const char* accum_name = nullptr, uint32_t view = 0) {
+    msm_accumulate<F>(pl, pts, ws, tm, accum_name, view);
+    msm_tail<F>(pl, ws, win_out);
   }
 
   // result = sum_w 2^(c w) (A_w + Wt_w) on the host
@@ -524,6 +616,7 @@ class Engine : public EngineBase {
     DevBuf<G2A> b2;
     DevBuf<G1A> fixed1;                          // alpha1, beta1, delta1, a_query[0], b_g1_query[0]
     DevBuf<G2A> fixed2;                          // beta2, delta2, b_g2_query[0]
+    DevBuf<uint8_t> skip;                        // per assignment index: bit0 = a_query point is infinity, bit1 = b_query point is infinity
     HG1A h_fixed1[5];                            // host copies (Montgomery form) for the serial tail
     HG2A h_fixed2[3];
   };
@@ -621,6 +714,12 @@ class Engine : public EngineBase {
       uint64_t j0 = p->lo > shift ? p->lo : shift;
       if (j0 < p->hi) pk_convert<Fq>(p->l.p + (j0 - p->lo), p->hi - j0);
     }
+    {  // infinity flags of the a / b query slices -> filtered MSM views (ark's mixed add skips infinity bases too)
+      p->skip.alloc(cnt ? cnt : 1);
+      uint8_t* fl = p->skip.p;
+      const G1A* pa = p->a.p; const G1A* pb = p->b1.p;
+      launch<k_pk_convert>(st_, cnt, ZKB_LAMBDA(size_t t) { fl[t] = (uint8_t)((pa[t].is_inf() ? 1 : 0) | (pb[t].is_inf() ? 2 : 0)); });
+    }
     d2h(st_, p->h_fixed1, p->fixed1.p, 5 * G1B);
     d2h(st_, p->h_fixed2, p->fixed2.p, 3 * G2B);
     stream_sync(st_);
@@ -661,7 +760,6 @@ class Engine : public EngineBase {
     } else if (!r.has_z) {
       throw Error(ZKB_E_ARG, "no resident assignment");
     }
-    witness_map_dev(r, tm);
     const size_t slot1 = 2 * MAXW * sizeof(G1X), slot2 = 2 * MAXW * sizeof(G2X);
     d_win_.ensure(4 * slot1 + slot2);
     G1X* w_h = (G1X*)d_win_.p;
@@ -669,26 +767,21 @@ class Engine : public EngineBase {
     G1X* w_a = (G1X*)(d_win_.p + 2 * slot1);
     G1X* w_b1 = (G1X*)(d_win_.p + 3 * slot1);
     G2X* w_b2 = (G2X*)(d_win_.p + 4 * slot1);
+    // z-dependent MSMs first: their tails then overlap the witness map and the h MSM
+    tm.begin("msm_plan_z");
+    plan_build(plan_z_, r.z_canon.p + 1 + pk.lo, pk.hi - pk.lo, 3, pk.skip.p);
+    tm.end();
+    msm_exec<Fq2>(plan_z_, pk.b2.p, w_b2, ws_[4], &tm, "accum1_g2_b2", 2);
+    msm_exec<Fq>(plan_z_, pk.l.p, w_l, ws_[1], &tm, "accum1_g1_l", 0);
+    msm_exec<Fq>(plan_z_, pk.a.p, w_a, ws_[2], &tm, "accum1_g1_a", 1);
+    msm_exec<Fq>(plan_z_, pk.b1.p, w_b1, ws_[3], &tm, "accum1_g1_b1", 2);
+    witness_map_dev(r, tm);
     tm.begin("msm_plan_h");
     plan_build(plan_h_, r.h.p + pk.hlo, pk.hhi - pk.hlo);
     tm.end();
-    tm.begin("msm_h");
-    msm_exec<Fq>(plan_h_, pk.h.p, w_h, &tm, "accum1_g1_h");
-    tm.end();
-    tm.begin("msm_plan_z");
-    plan_build(plan_z_, r.z_canon.p + 1 + pk.lo, pk.hi - pk.lo);
-    tm.end();
-    tm.begin("msm_l");
-    msm_exec<Fq>(plan_z_, pk.l.p, w_l, &tm, "accum1_g1_l");
-    tm.end();
-    tm.begin("msm_a");
-    msm_exec<Fq>(plan_z_, pk.a.p, w_a, &tm, "accum1_g1_a");
-    tm.end();
-    tm.begin("msm_b1");
-    msm_exec<Fq>(plan_z_, pk.b1.p, w_b1, &tm, "accum1_g1_b1");
-    tm.end();
-    tm.begin("msm_b2");
-    msm_exec<Fq2>(plan_z_, pk.b2.p, w_b2, &tm, "accum1_g2_b2");
+    msm_exec<Fq>(plan_h_, pk.h.p, w_h, ws_[0], &tm, "accum1_g1_h", 0);
+    tm.begin("tails_wait");
+    for (int k = 0; k < 5; k++) ws_[k].tail_done.wait(st_);
     tm.end();
     std::vector<uint8_t> hw(4 * slot1 + slot2);
     tm.begin("d2h_windows");
@@ -796,7 +889,8 @@ class Engine : public EngineBase {
     plan_build(plan_misc_, msm_scalars_.p, n);
     tm.end();
     tm.begin("msm_exec");
-    msm_exec<F>(plan_misc_, pts, (X*)d_win_.p, &tm, "accum1");
+    msm_exec<F>(plan_misc_, pts, (X*)d_win_.p, ws_[5], &tm, "accum1");
+    ws_[5].tail_done.wait(st_);
     tm.end();
     std::vector<uint8_t> hw(2 * MAXW * sizeof(X));
     d2h(st_, hw.data(), d_win_.p, hw.size());

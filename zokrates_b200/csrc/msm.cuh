@@ -49,12 +49,17 @@ ZKB_HD uint32_t scalar_bits(const uint32_t* s, uint32_t lo, uint32_t cnt) {
 
 // ---- digits + histogram: one thread per scalar -------------------------------------------------
 // digits[w * n + i] = (|d| - 1) | sign, or MSM_NONE when d == 0.
-ZKB_HDN inline void msm_digits_body(MsmShape sh, const uint32_t* scalars /* n x 8, canonical */, uint32_t* digits,
-                                    uint32_t* counts, uint32_t i) {
+// Views: one digit decomposition can feed several sorted lists that differ in which points they skip
+// (view 0 keeps everything; view v > 0 drops pair i when bit (v-1) of skip[i] is set — the points that are
+// the point at infinity in that query vector, which ark's add_assign_mixed also treats as a no-op).
+ZKB_HDN inline void msm_digits_body(MsmShape sh, uint32_t nviews, const uint8_t* skip, const uint32_t* scalars /* n x 8, canonical */,
+                                    uint32_t* digits, uint32_t* counts /* nviews x W*B */, uint32_t i) {
   if (i >= sh.n) return;
   uint32_t s[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) s[k] = scalars[(size_t)i * 8 + k];
+  const uint32_t sk = skip ? skip[i] : 0;
+  const uint32_t NB = sh.W * sh.B;
   uint32_t carry = 0;
   const uint32_t full = 1u << sh.c, half = sh.B;
   for (uint32_t w = 0; w < sh.W; w++) {
@@ -74,20 +79,35 @@ ZKB_HDN inline void msm_digits_body(MsmShape sh, const uint32_t* scalars /* n x 
       carry = 0;
     }
     digits[(size_t)w * sh.n + i] = code;
-    if (code != MSM_NONE) zkb_atomic_add(&counts[w * sh.B + (code & ~MSM_NEG)], 1);
+    if (code != MSM_NONE) {
+      const uint32_t key = w * sh.B + (code & ~MSM_NEG);
+      zkb_atomic_add(&counts[key], 1);
+      for (uint32_t v = 1; v < nviews; v++)
+        if (!((sk >> (v - 1)) & 1u)) zkb_atomic_add(&counts[(size_t)v * NB + key], 1);
+    }
   }
 }
 
 // ---- scatter: one thread per (window, scalar) --------------------------------------------------
-ZKB_HDN inline void msm_scatter_body(MsmShape sh, const uint32_t* digits, const uint32_t* offsets, uint32_t* cursor,
-                                     uint32_t* sorted, size_t t) {
-  if (t >= (size_t)sh.n * sh.W) return;
+// offsets: nviews x (NB+1), cursor: nviews x NB, sorted: nviews x (n*W)
+ZKB_HDN inline void msm_scatter_body(MsmShape sh, uint32_t nviews, const uint8_t* skip, const uint32_t* digits,
+                                     const uint32_t* offsets, uint32_t* cursor, uint32_t* sorted, size_t t) {
+  const size_t total = (size_t)sh.n * sh.W;
+  if (t >= total) return;
   uint32_t code = digits[t];
   if (code == MSM_NONE) return;
+  const uint32_t NB = sh.W * sh.B;
   uint32_t w = (uint32_t)(t / sh.n), i = (uint32_t)(t % sh.n);
   uint32_t key = w * sh.B + (code & ~MSM_NEG);
+  const uint32_t sk = skip ? skip[i] : 0;
+  const uint32_t val = i | (code & MSM_NEG);
   uint32_t pos = zkb_atomic_add(&cursor[key], 1);
-  sorted[offsets[key] + pos] = i | (code & MSM_NEG);
+  sorted[offsets[key] + pos] = val;
+  for (uint32_t v = 1; v < nviews; v++)
+    if (!((sk >> (v - 1)) & 1u)) {
+      uint32_t p2 = zkb_atomic_add(&cursor[(size_t)v * NB + key], 1);
+      sorted[(size_t)v * total + offsets[(size_t)v * (NB + 1) + key] + p2] = val;
+    }
 }
 
 // ---- level-1 accumulate: affine points, keys implied by the offsets array -----------------------

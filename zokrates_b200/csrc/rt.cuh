@@ -89,6 +89,23 @@ inline void dev_fill_ff(Stream st, void* p, size_t bytes) {
   if (bytes) ZKB_CUDA(cudaMemsetAsync(p, 0xff, bytes, st.s));
 }
 inline void stream_sync(Stream st) { ZKB_CUDA(cudaStreamSynchronize(st.s)); }
+// side streams (high priority: their small latency-bound kernels are scheduled ahead of the pending blocks of
+// a big kernel on the main stream) and cross-stream ordering
+inline Stream stream_create_high_priority() {
+  int lo = 0, hi = 0;
+  ZKB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  Stream s;
+  ZKB_CUDA(cudaStreamCreateWithPriority(&s.s, cudaStreamNonBlocking, hi));
+  return s;
+}
+inline void stream_destroy(Stream s) { if (s.s) cudaStreamDestroy(s.s); }
+struct Event {
+  cudaEvent_t e = nullptr;
+  void ensure() { if (!e) ZKB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); }
+  void record(Stream s) { ensure(); ZKB_CUDA(cudaEventRecord(e, s.s)); }
+  void wait(Stream s) { if (e) ZKB_CUDA(cudaStreamWaitEvent(s.s, e, 0)); }
+  void destroy() { if (e) { cudaEventDestroy(e); e = nullptr; } }
+};
 
 #else  // ------------------------------------------------------------------ host emulation (tests)
 
@@ -117,6 +134,13 @@ inline void d2d(Stream, void* dst, const void* src, size_t bytes) { memmove(dst,
 inline void dev_zero(Stream, void* p, size_t bytes) { memset(p, 0, bytes); }
 inline void dev_fill_ff(Stream, void* p, size_t bytes) { memset(p, 0xff, bytes); }
 inline void stream_sync(Stream) {}
+inline Stream stream_create_high_priority() { return Stream(); }
+inline void stream_destroy(Stream) {}
+struct Event {
+  void record(Stream) {}
+  void wait(Stream) {}
+  void destroy() {}
+};
 
 #endif
 
