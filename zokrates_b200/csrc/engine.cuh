@@ -18,6 +18,10 @@
 #include "rt.cuh"
 #include "engine_base.cuh"
 
+#ifndef ZKB_G2_MINB
+#define ZKB_G2_MINB 3
+#endif
+
 namespace zkb {
 
 // kernel name tags (show up in ncu / nsys kernel names)
@@ -540,7 +544,15 @@ class Engine : public EngineBase {
     const uint32_t* so = pl.sorted.p + (size_t)view * pl.sh.n * pl.sh.W;
     uint32_t* k0 = ws.key[0].p; X* v0 = (X*)ws.val[0].p;
     if (tm && accum_name) tm->begin(accum_name);
-    launch<k_msm_accum1>(st_, nt1, ZKB_LAMBDA(size_t t) { msm_accum1_body<F>(NB, T1, of, so, pts, buckets, k0, v0, nt1, (uint32_t)t); });
+    // G2 (Fq2 coordinates) wants > 200 registers: cap it so that 3 blocks (12 warps) stay resident per SM
+    if (sizeof(F) > sizeof(Fq)) {
+      static const int minb = getenv("ZKB_G2_MINB") ? atoi(getenv("ZKB_G2_MINB")) : ZKB_G2_MINB;  // tuning knob
+      if (minb >= 4) launch<k_msm_accum1, 128, 4>(st_, nt1, ZKB_LAMBDA(size_t t) { msm_accum1_body<F>(NB, T1, of, so, pts, buckets, k0, v0, nt1, (uint32_t)t); });
+      else if (minb == 3) launch<k_msm_accum1, 128, 3>(st_, nt1, ZKB_LAMBDA(size_t t) { msm_accum1_body<F>(NB, T1, of, so, pts, buckets, k0, v0, nt1, (uint32_t)t); });
+      else launch<k_msm_accum1, 128, 2>(st_, nt1, ZKB_LAMBDA(size_t t) { msm_accum1_body<F>(NB, T1, of, so, pts, buckets, k0, v0, nt1, (uint32_t)t); });
+    } else {
+      launch<k_msm_accum1>(st_, nt1, ZKB_LAMBDA(size_t t) { msm_accum1_body<F>(NB, T1, of, so, pts, buckets, k0, v0, nt1, (uint32_t)t); });
+    }
     if (tm && accum_name) tm->end();
     ws.acc_done.record(st_);
   }

@@ -41,8 +41,8 @@ struct Stream {
   cudaStream_t s = nullptr;
 };
 
-template <class Tag, class Fn>
-__global__ void zkb_kernel(size_t n, Fn fn) {
+template <class Tag, int BLOCK, int MINB, class Fn>
+__global__ void __launch_bounds__(BLOCK, MINB) zkb_kernel(size_t n, Fn fn) {
   size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid < n) fn(tid);
 }
@@ -54,13 +54,13 @@ inline uint64_t& launch_counter() {
   return c;
 }
 
-template <class Tag, int BLOCK = 128, class Fn>
+template <class Tag, int BLOCK = 128, int MINB = 1, class Fn>
 inline void launch(Stream st, size_t n, Fn fn) {
   if (n == 0) return;
   launch_counter()++;
   size_t blocks = (n + BLOCK - 1) / BLOCK;
   if (blocks > 0x7fffffffull) throw Error(ZKB_E_ARG, "grid too large");
-  zkb_kernel<Tag, Fn><<<(unsigned)blocks, BLOCK, 0, st.s>>>(n, fn);
+  zkb_kernel<Tag, BLOCK, MINB, Fn><<<(unsigned)blocks, BLOCK, 0, st.s>>>(n, fn);
   ZKB_CUDA(cudaGetLastError());
 }
 
@@ -117,7 +117,7 @@ inline uint64_t& launch_counter() {
   static uint64_t c = 0;
   return c;
 }
-template <class Tag, int BLOCK = 128, class Fn>
+template <class Tag, int BLOCK = 128, int MINB = 1, class Fn>
 inline void launch(Stream, size_t n, Fn fn) {
   if (n) launch_counter()++;
   for (size_t tid = 0; tid < n; tid++) fn(tid);
