@@ -1,3 +1,4 @@
+#define _GNU_SOURCE
 /* zkoracle.c — CPU restatement (C, OpenMP) of the reference's Groth16 proving path.
  *
  * TEST INFRASTRUCTURE / CPU BASELINE ONLY: loaded by tests/, __graft_entry__.smoke() and bench.py's
@@ -28,6 +29,7 @@
 #endif
 
 typedef unsigned __int128 u128;
+static int zko_pool_threads(void);
 #define MAXL 6
 
 typedef struct { uint64_t l[MAXL]; } fe;
@@ -169,6 +171,7 @@ static int curves_ready = 0;
 
 static void curves_init(void) {
   if (curves_ready) return;
+  zko_pool_threads();
   static const uint64_t bn_r[4] = {0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
   static const uint64_t bn_p[4] = {0x3c208c16d87cfd47ull, 0x97816a916871ca8dull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
   static const uint64_t bls_r[4] = {0xffffffff00000001ull, 0x53bda402fffe5bfeull, 0x3339d80809a1d805ull, 0x73eda753299d7d48ull};
@@ -189,6 +192,27 @@ static void curves_init(void) {
   curves_ready = 1;
 }
 
+/* OpenMP team size: never more than the CPUs this process may actually run on (affinity mask and cgroup quota) —
+ * an oversubscribed team spends its time in barriers. */
+#include <sched.h>
+static int zko_pool_threads(void) {
+  static int cached = 0;
+  if (cached) return cached;
+  int n = 1;
+#ifdef _OPENMP
+  n = omp_get_max_threads();
+#endif
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof set, &set) == 0) { int k = CPU_COUNT(&set); if (k > 0 && k < n) n = k; }
+  FILE* fp = fopen("/sys/fs/cgroup/cpu.max", "r");
+  if (fp) { long long q = -1, per = 0; char buf[64]; if (fscanf(fp, "%63s %lld", buf, &per) == 2 && strcmp(buf, "max") != 0) { q = atoll(buf); if (q > 0 && per > 0) { int k = (int)((q + per - 1) / per); if (k >= 1 && k < n) n = k; } } fclose(fp); }
+  if (n < 1) n = 1;
+#ifdef _OPENMP
+  omp_set_num_threads(n);
+#endif
+  cached = n;
+  return n;
+}
 static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
 /* canonical little-endian bytes <-> Montgomery element */
@@ -234,27 +258,40 @@ static void g2_write(const curve_t* c, uint8_t* b, const g2_aff* p) {
 static void fr_fft(const curve_t* c, fe* a, int log_n, const fe* omega) {
   const fctx* f = &c->fr;
   size_t n = (size_t)1 << log_n;
-  for (size_t k = 0; k < n; k++) {  /* bit-reversal permutation */
-    size_t rk = 0; for (int b = 0; b < log_n; b++) rk |= ((k >> b) & 1) << (log_n - 1 - b);
-    if (k < rk) { fe t = a[k]; a[k] = a[rk]; a[rk] = t; }
+  if (n == 1) return;
+  /* twiddles w^k, k < n/2, built in parallel chunks (ark: roots of unity computed with rayon per call) */
+  size_t half_n = n >> 1;
+  fe* tw = (fe*)malloc(half_n * sizeof(fe));
+  int nt = zko_pool_threads();
+  size_t chunk = (half_n + nt - 1) / nt;
+#pragma omp parallel for schedule(static) num_threads(nt)
+  for (int t = 0; t < nt; t++) {
+    size_t lo = (size_t)t * chunk, hi = lo + chunk < half_n ? lo + chunk : half_n;
+    if (lo >= hi) continue;
+    uint64_t e[1] = {lo};
+    fe p; fe_pow(f, &p, omega, e, 1);
+    for (size_t k = lo; k < hi; k++) { tw[k] = p; fe_mul(f, &p, &p, omega); }
   }
-  for (int s = 1; s <= log_n; s++) {
-    size_t m = (size_t)1 << s, half = m >> 1;
-    fe wm = *omega;
-    for (int i = s; i < log_n; i++) fe_sqr(f, &wm, &wm);   /* omega^(n/m) */
-    fe* tw = (fe*)malloc(half * sizeof(fe));
-    tw[0] = f->r1;
-    for (size_t j = 1; j < half; j++) fe_mul(f, &tw[j], &tw[j - 1], &wm);
-#pragma omp parallel for schedule(static)
-    for (size_t k = 0; k < n / 2; k++) {
-      size_t blk = k / half, j = k % half, i0 = blk * m + j;
-      fe t, u = a[i0];
-      fe_mul(f, &t, &a[i0 + half], &tw[j]);
-      fe_add(f, &a[i0], &u, &t);
-      fe_sub(f, &a[i0 + half], &u, &t);
+#pragma omp parallel num_threads(nt)
+  {
+#pragma omp for schedule(static)
+    for (size_t k = 0; k < n; k++) {  /* bit-reversal permutation */
+      size_t rk = 0; for (int b = 0; b < log_n; b++) rk |= ((k >> b) & 1) << (log_n - 1 - b);
+      if (k < rk) { fe t = a[k]; a[k] = a[rk]; a[rk] = t; }
     }
-    free(tw);
+    for (int s = 1; s <= log_n; s++) {
+      size_t m = (size_t)1 << s, half = m >> 1, stride = n / m;
+#pragma omp for schedule(static)
+      for (size_t k = 0; k < n / 2; k++) {
+        size_t blk = k / half, j = k % half, i0 = blk * m + j;
+        fe t, u = a[i0];
+        fe_mul(f, &t, &a[i0 + half], &tw[j * stride]);
+        fe_add(f, &a[i0], &u, &t);
+        fe_sub(f, &a[i0 + half], &u, &t);
+      }
+    }
   }
+  free(tw);
 }
 static void domain_omega(const curve_t* c, int log_n, fe* w) {
   *w = c->root;
@@ -344,13 +381,7 @@ static fe* witness_map(const curve_t* c, const r1cs_t* r, const fe* z, int* log_
 /* ------------------------------------------------------------------------------------------- exported API */
 #define EXPORT __attribute__((visibility("default")))
 
-EXPORT int zko_threads(void) {
-#ifdef _OPENMP
-  return omp_get_max_threads();
-#else
-  return 1;
-#endif
-}
+EXPORT int zko_threads(void) { return zko_pool_threads(); }
 EXPORT void zko_set_threads(int n) {
 #ifdef _OPENMP
   if (n > 0) omp_set_num_threads(n);

@@ -19,7 +19,7 @@
 #include "engine_base.cuh"
 
 #ifndef ZKB_G2_MINB
-#define ZKB_G2_MINB 3
+#define ZKB_G2_MINB 2
 #endif
 
 namespace zkb {
@@ -520,12 +520,23 @@ class Engine : public EngineBase {
   };
   static constexpr int NUM_WS = 6;   // h, l, a, b1, b2, misc
   MsmWs ws_[NUM_WS];
+  // witness map + h-plan run on their own stream underneath the z-dependent MSMs
+  Stream wm_stream_;
+  bool has_wm_stream_ = false;
+  Event ev_z_ready_, ev_h_ready_;
+  struct StreamScope {  // temporarily redirect every helper that launches on st_
+    Stream& ref; Stream saved;
+    StreamScope(Stream& r, Stream s) : ref(r), saved(r) { ref = s; }
+    ~StreamScope() { ref = saved; }
+  };
   Stream tail_stream(MsmWs& ws) {
     if (!ws.has_stream) { ws.tail = stream_create_high_priority(); ws.has_stream = true; }
     return ws.tail;
   }
   ~Engine() override {
     for (auto& w : ws_) { if (w.has_stream) stream_destroy(w.tail); w.acc_done.destroy(); w.tail_done.destroy(); }
+    if (has_wm_stream_) stream_destroy(wm_stream_);
+    ev_z_ready_.destroy(); ev_h_ready_.destroy();
   }
 
   // phase 1 (main stream): bucket accumulation of one MSM.  Throughput-bound (INT32 multiply pipe).
@@ -779,7 +790,20 @@ class Engine : public EngineBase {
     G1X* w_a = (G1X*)(d_win_.p + 2 * slot1);
     G1X* w_b1 = (G1X*)(d_win_.p + 3 * slot1);
     G2X* w_b2 = (G2X*)(d_win_.p + 4 * slot1);
-    // z-dependent MSMs first: their tails then overlap the witness map and the h MSM
+    // The witness map (3 SpMV, 7 NTT, latency/bandwidth-bound at this size) and the h digit plan go to a second
+    // stream and fill the multiply-pipe bubbles of the z-dependent MSMs running on the main stream.
+    if (!has_wm_stream_) { wm_stream_ = stream_create(); has_wm_stream_ = true; }
+    ev_z_ready_.record(st_);
+    StageTimer tm2(wm_stream_);
+    {
+      StreamScope sc(st_, wm_stream_);
+      ev_z_ready_.wait(st_);
+      witness_map_dev(r, tm2);
+      tm2.begin("msm_plan_h");
+      plan_build(plan_h_, r.h.p + pk.hlo, pk.hhi - pk.hlo);
+      tm2.end();
+      ev_h_ready_.record(st_);
+    }
     tm.begin("msm_plan_z");
     plan_build(plan_z_, r.z_canon.p + 1 + pk.lo, pk.hi - pk.lo, 3, pk.skip.p);
     tm.end();
@@ -787,9 +811,8 @@ class Engine : public EngineBase {
     msm_exec<Fq>(plan_z_, pk.l.p, w_l, ws_[1], &tm, "accum1_g1_l", 0);
     msm_exec<Fq>(plan_z_, pk.a.p, w_a, ws_[2], &tm, "accum1_g1_a", 1);
     msm_exec<Fq>(plan_z_, pk.b1.p, w_b1, ws_[3], &tm, "accum1_g1_b1", 2);
-    witness_map_dev(r, tm);
-    tm.begin("msm_plan_h");
-    plan_build(plan_h_, r.h.p + pk.hlo, pk.hhi - pk.hlo);
+    tm.begin("wait_h");
+    ev_h_ready_.wait(st_);
     tm.end();
     msm_exec<Fq>(plan_h_, pk.h.p, w_h, ws_[0], &tm, "accum1_g1_h", 0);
     tm.begin("tails_wait");
@@ -801,6 +824,11 @@ class Engine : public EngineBase {
     tm.end();
     stream_sync(st_);
     tm.collect(timings);
+    {
+      std::vector<std::pair<const char*, double>> t2;
+      tm2.collect(t2);
+      for (auto& e : t2) timings.push_back(e);
+    }
     HostPartial hp;
     auto hor1 = [&](size_t k, const MsmPlan& pl) {
       return pl.sh.n ? host_horner<HG1X>((const HG1X*)(hw.data() + k * slot1), pl.sh.W, pl.sh.c) : HG1X::identity();

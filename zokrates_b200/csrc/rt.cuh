@@ -98,6 +98,11 @@ inline Stream stream_create_high_priority() {
   ZKB_CUDA(cudaStreamCreateWithPriority(&s.s, cudaStreamNonBlocking, hi));
   return s;
 }
+inline Stream stream_create() {
+  Stream s;
+  ZKB_CUDA(cudaStreamCreateWithFlags(&s.s, cudaStreamNonBlocking));
+  return s;
+}
 inline void stream_destroy(Stream s) { if (s.s) cudaStreamDestroy(s.s); }
 struct Event {
   cudaEvent_t e = nullptr;
@@ -135,6 +140,7 @@ inline void dev_zero(Stream, void* p, size_t bytes) { memset(p, 0, bytes); }
 inline void dev_fill_ff(Stream, void* p, size_t bytes) { memset(p, 0xff, bytes); }
 inline void stream_sync(Stream) {}
 inline Stream stream_create_high_priority() { return Stream(); }
+inline Stream stream_create() { return Stream(); }
 inline void stream_destroy(Stream) {}
 struct Event {
   void record(Stream) {}
