@@ -29,7 +29,7 @@ struct k_fr_convert; struct k_spmv; struct k_ntt_dif; struct k_ntt_dit; struct k
 struct k_ntt_table; struct k_qap_pointwise; struct k_msm_digits; struct k_msm_scatter; struct k_msm_accum1;
 struct k_msm_accum2; struct k_msm_tree; struct k_msm_horner; struct k_pk_convert; struct k_final_a; struct k_final_b;
 struct k_final_c; struct k_final_d; struct k_point_out; struct k_field_op; struct k_setup_scalars; struct k_fixed_base;
-struct k_to_affine; struct k_copy;
+struct k_to_affine; struct k_copy; struct k_msm_table;
 
 // ---------------------------------------------------------------------------------------------
 // stage timer: CUDA events on the engine stream (no-op in the host emulation)
@@ -163,7 +163,7 @@ inline void exclusive_scan(Stream st, const uint32_t* counts, uint32_t* offsets,
 
 // ---------------------------------------------------------------------------------------------
 struct MsmPlan {
-  MsmShape sh{0, 0, 0, 0};
+  MsmShape sh{0, 0, 0, 0, 0};
   uint32_t nbuckets = 0;
   uint32_t T1 = 32, T2 = 32;
   uint32_t nt1 = 0;  // level-1 chunks
@@ -177,6 +177,19 @@ inline uint32_t msm_pick_c(uint64_t n, int fr_bits) {
   for (uint32_t c = 4; c <= 16; c++) {
     double W = (double)((fr_bits + 1 + c - 1) / c);
     double cost = W * (10.0 * (double)n + 40.0 * (double)(1u << (c - 1)));
+    if (cost < best_cost) { best_cost = cost; best = c; }
+  }
+  return best;
+}
+
+// with precomputed window multiples all windows share one bucket set, so larger windows pay off
+inline uint32_t msm_pick_c_pre(uint64_t n, int fr_bits) {
+  uint32_t best = 4;
+  double best_cost = 1e300;
+  for (uint32_t c = 4; c <= 22; c++) {
+    uint64_t W = (fr_bits + 1 + c - 1) / c;
+    if (W > 64 || n * W >= (1ull << 31)) continue;
+    double cost = (double)W * 10.0 * (double)n + 40.0 * (double)(1u << (c - 1));
     if (cost < best_cost) { best_cost = cost; best = c; }
   }
   return best;
@@ -475,15 +488,17 @@ class Engine : public EngineBase {
 
   // ------------------------------------------------------------------------------ MSM
 
-  void plan_build(MsmPlan& pl, const Fr* scalars, uint64_t n, uint32_t nviews = 1, const uint8_t* skip = nullptr) {
+  void plan_build(MsmPlan& pl, const Fr* scalars, uint64_t n, uint32_t nviews = 1, const uint8_t* skip = nullptr,
+                  uint32_t pre_c = 0 /* != 0: precomputed window tables with this c */) {
     pl.sh.n = (uint32_t)n;
     pl.nviews = nviews;
+    pl.sh.pre = pre_c ? 1 : 0;
     if (n == 0) return;
-    uint32_t c = msm_pick_c(n, C::FR_BITS);
+    uint32_t c = pre_c ? pre_c : msm_pick_c(n, C::FR_BITS);
     pl.sh.c = c;
     pl.sh.W = (C::FR_BITS + 1 + c - 1) / c;
     pl.sh.B = 1u << (c - 1);
-    pl.nbuckets = pl.sh.W * pl.sh.B;
+    pl.nbuckets = msm_nbuckets(pl.sh);
     uint64_t total = n * pl.sh.W;
     if (total * nviews >= (1ull << 32)) throw Error(ZKB_E_ARG, "msm too large");
     // chunk size: aim for several waves of resident threads, at least 8 entries per chunk
@@ -577,7 +592,7 @@ class Engine : public EngineBase {
     if (pl.sh.n == 0) return;
     Stream ts = tail_stream(ws);
     ws.acc_done.wait(ts);
-    const uint32_t W = pl.sh.W, B = pl.sh.B, T2 = pl.T2, nt1 = pl.nt1;
+    const uint32_t W = pl.sh.pre ? 1 : pl.sh.W, B = pl.sh.B, T2 = pl.T2, nt1 = pl.nt1;
     X* buckets = (X*)ws.buckets.p;
     uint32_t L = 2 * nt1;
     int cur = 0;
@@ -639,6 +654,7 @@ class Engine : public EngineBase {
     DevBuf<G2A> b2;
     DevBuf<G1A> fixed1;                          // alpha1, beta1, delta1, a_query[0], b_g1_query[0]
     DevBuf<G2A> fixed2;                          // beta2, delta2, b_g2_query[0]
+    uint32_t pre_cz = 0, pre_ch = 0;             // != 0: a/b1/b2/l (resp. h) hold W window tables 2^(c w) P (HBM-resident precomputation)
     DevBuf<uint8_t> skip;                        // per assignment index: bit0 = a_query point is infinity, bit1 = b_query point is infinity
     HG1A h_fixed1[5];                            // host copies (Montgomery form) for the serial tail
     HG2A h_fixed2[3];
@@ -666,6 +682,51 @@ class Engine : public EngineBase {
       }
       pts[t] = p;
     });
+  }
+
+  // B200-first: the query vectors are fixed per key and HBM is large, so keep 2^(c w) P_i for every window w
+  // resident.  All windows of an MSM then share one bucket set: larger windows (fewer mixed additions per
+  // scalar), a 16x smaller bucket tree, and no 2^(c w) Horner at the end.
+  template <class F>
+  void build_table(DevBuf<Affine<F>>& buf, size_t n, uint32_t c, uint32_t W) {
+    DevBuf<Affine<F>> tab(n * W);
+    const Affine<F>* src = buf.p;
+    Affine<F>* dst = tab.p;
+    launch<k_msm_table>(st_, n, ZKB_LAMBDA(size_t t) { msm_table_body<F, 16>(src, dst, (uint32_t)n, c, W, (uint32_t)t); });
+    stream_sync(st_);
+    buf = std::move(tab);
+  }
+  void precompute_tables(Pk& p) {
+    const char* env = getenv("ZKB_PRECOMP");
+    if (env && atoi(env) == 0) return;
+    const uint64_t cnt = p.hi - p.lo, hcnt = p.hhi - p.hlo;
+    auto plan = [&](uint64_t n, uint32_t& c, uint32_t& W) {
+      c = 0; W = 0;
+      const char* emin = getenv("ZKB_PRECOMP_MIN");   // test hooks: minimum size / forced window width
+      const char* ec = getenv("ZKB_PRECOMP_C");
+      if (n < (uint64_t)(emin ? atoll(emin) : (1 << 14))) return;   // small MSMs are latency-bound; tables buy nothing
+      uint32_t cc = ec ? (uint32_t)atoi(ec) : msm_pick_c_pre(n, C::FR_BITS);
+      uint32_t ww = (C::FR_BITS + 1 + cc - 1) / cc;
+      if (ww > 16) return;
+      c = cc; W = ww;
+    };
+    uint32_t cz, Wz, ch, Wh;
+    plan(cnt, cz, Wz);
+    plan(hcnt, ch, Wh);
+    size_t need = (size_t)Wz * cnt * (3 * G1B + G2B) + (size_t)Wh * hcnt * G1B;
+#if !defined(ZKB_EMU)
+    size_t free_b = 0, total_b = 0;
+    ZKB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    if (need > free_b / 2) return;             // keep room for the sort buffers and other keys
+#else
+    (void)need;
+#endif
+    if (cz) {
+      build_table<Fq>(p.a, cnt, cz, Wz); build_table<Fq>(p.b1, cnt, cz, Wz); build_table<Fq>(p.l, cnt, cz, Wz);
+      build_table<Fq2>(p.b2, cnt, cz, Wz);
+      p.pre_cz = cz;
+    }
+    if (ch) { build_table<Fq>(p.h, hcnt, ch, Wh); p.pre_ch = ch; }
   }
 
   uint64_t pk_load(const uint8_t* pk, size_t len, uint32_t rank, uint32_t world) override {
@@ -743,6 +804,7 @@ class Engine : public EngineBase {
       const G1A* pa = p->a.p; const G1A* pb = p->b1.p;
       launch<k_pk_convert>(st_, cnt, ZKB_LAMBDA(size_t t) { fl[t] = (uint8_t)((pa[t].is_inf() ? 1 : 0) | (pb[t].is_inf() ? 2 : 0)); });
     }
+    precompute_tables(*p);
     d2h(st_, p->h_fixed1, p->fixed1.p, 5 * G1B);
     d2h(st_, p->h_fixed2, p->fixed2.p, 3 * G2B);
     stream_sync(st_);
@@ -792,7 +854,12 @@ class Engine : public EngineBase {
     G2X* w_b2 = (G2X*)(d_win_.p + 4 * slot1);
     // The witness map (3 SpMV, 7 NTT, latency/bandwidth-bound at this size) and the h digit plan go to a second
     // stream and fill the multiply-pipe bubbles of the z-dependent MSMs running on the main stream.
-    if (!has_wm_stream_) { wm_stream_ = stream_create(); has_wm_stream_ = true; }
+    if (!has_wm_stream_) {
+      // high priority by default: its small kernels slot in between the blocks of the big accumulate kernels
+      const char* e = getenv("ZKB_WM_PRIO");
+      wm_stream_ = (e && atoi(e) == 0) ? stream_create() : stream_create_high_priority();
+      has_wm_stream_ = true;
+    }
     ev_z_ready_.record(st_);
     StageTimer tm2(wm_stream_);
     {
@@ -800,12 +867,12 @@ class Engine : public EngineBase {
       ev_z_ready_.wait(st_);
       witness_map_dev(r, tm2);
       tm2.begin("msm_plan_h");
-      plan_build(plan_h_, r.h.p + pk.hlo, pk.hhi - pk.hlo);
+      plan_build(plan_h_, r.h.p + pk.hlo, pk.hhi - pk.hlo, 1, nullptr, pk.pre_ch);
       tm2.end();
       ev_h_ready_.record(st_);
     }
     tm.begin("msm_plan_z");
-    plan_build(plan_z_, r.z_canon.p + 1 + pk.lo, pk.hi - pk.lo, 3, pk.skip.p);
+    plan_build(plan_z_, r.z_canon.p + 1 + pk.lo, pk.hi - pk.lo, 3, pk.skip.p, pk.pre_cz);
     tm.end();
     msm_exec<Fq2>(plan_z_, pk.b2.p, w_b2, ws_[4], &tm, "accum1_g2_b2", 2);
     msm_exec<Fq>(plan_z_, pk.l.p, w_l, ws_[1], &tm, "accum1_g1_l", 0);
@@ -831,10 +898,10 @@ class Engine : public EngineBase {
     }
     HostPartial hp;
     auto hor1 = [&](size_t k, const MsmPlan& pl) {
-      return pl.sh.n ? host_horner<HG1X>((const HG1X*)(hw.data() + k * slot1), pl.sh.W, pl.sh.c) : HG1X::identity();
+      return pl.sh.n ? host_horner<HG1X>((const HG1X*)(hw.data() + k * slot1), pl.sh.pre ? 1 : pl.sh.W, pl.sh.c) : HG1X::identity();
     };
     hp.h = hor1(0, plan_h_); hp.l = hor1(1, plan_z_); hp.a = hor1(2, plan_z_); hp.b1 = hor1(3, plan_z_);
-    hp.b2 = plan_z_.sh.n ? host_horner<HG2X>((const HG2X*)(hw.data() + 4 * slot1), plan_z_.sh.W, plan_z_.sh.c)
+    hp.b2 = plan_z_.sh.n ? host_horner<HG2X>((const HG2X*)(hw.data() + 4 * slot1), plan_z_.sh.pre ? 1 : plan_z_.sh.W, plan_z_.sh.c)
                          : HG2X::identity();
     memcpy(partial_out, &hp, sizeof hp);
   }

@@ -34,6 +34,7 @@ struct Fp2T {
     B r0 = B::mul(B::add(a.c0, a.c1), B::sub(a.c0, a.c1));
     return Fp2{r0, B::dbl(t)};
   }
+  ZKB_NI static Fp2 mul_ni(const Fp2& a, const Fp2& b) { return mul(a, b); }
   ZKB_NI static Fp2 inv(const Fp2& a) {
     B d = B::inv(B::add(B::sqr(a.c0), B::sqr(a.c1)));
     return Fp2{B::mul(a.c0, d), B::neg(B::mul(a.c1, d))};

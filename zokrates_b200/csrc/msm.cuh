@@ -37,7 +37,9 @@ struct MsmShape {
   uint32_t c;        // window bits
   uint32_t W;        // windows
   uint32_t B;        // buckets per window = 2^(c-1)
+  uint32_t pre;      // 1: the point table holds 2^(c w) P_i at index w*n + i, so all windows share ONE bucket set
 };
+ZKB_HD uint32_t msm_nbuckets(const MsmShape& sh) { return sh.pre ? sh.B : sh.W * sh.B; }
 
 ZKB_HD uint32_t scalar_bits(const uint32_t* s, uint32_t lo, uint32_t cnt) {
   // bits [lo, lo+cnt) of a 256-bit little-endian scalar, cnt <= 31
@@ -59,7 +61,7 @@ ZKB_HDN inline void msm_digits_body(MsmShape sh, uint32_t nviews, const uint8_t*
 #pragma unroll
   for (int k = 0; k < 8; k++) s[k] = scalars[(size_t)i * 8 + k];
   const uint32_t sk = skip ? skip[i] : 0;
-  const uint32_t NB = sh.W * sh.B;
+  const uint32_t NB = msm_nbuckets(sh);
   uint32_t carry = 0;
   const uint32_t full = 1u << sh.c, half = sh.B;
   for (uint32_t w = 0; w < sh.W; w++) {
@@ -80,7 +82,7 @@ ZKB_HDN inline void msm_digits_body(MsmShape sh, uint32_t nviews, const uint8_t*
     }
     digits[(size_t)w * sh.n + i] = code;
     if (code != MSM_NONE) {
-      const uint32_t key = w * sh.B + (code & ~MSM_NEG);
+      const uint32_t key = (sh.pre ? 0u : w * sh.B) + (code & ~MSM_NEG);
       zkb_atomic_add(&counts[key], 1);
       for (uint32_t v = 1; v < nviews; v++)
         if (!((sk >> (v - 1)) & 1u)) zkb_atomic_add(&counts[(size_t)v * NB + key], 1);
@@ -96,11 +98,11 @@ ZKB_HDN inline void msm_scatter_body(MsmShape sh, uint32_t nviews, const uint8_t
   if (t >= total) return;
   uint32_t code = digits[t];
   if (code == MSM_NONE) return;
-  const uint32_t NB = sh.W * sh.B;
+  const uint32_t NB = msm_nbuckets(sh);
   uint32_t w = (uint32_t)(t / sh.n), i = (uint32_t)(t % sh.n);
-  uint32_t key = w * sh.B + (code & ~MSM_NEG);
+  uint32_t key = (sh.pre ? 0u : w * sh.B) + (code & ~MSM_NEG);
   const uint32_t sk = skip ? skip[i] : 0;
-  const uint32_t val = i | (code & MSM_NEG);
+  const uint32_t val = (sh.pre ? w * sh.n + i : i) | (code & MSM_NEG);
   uint32_t pos = zkb_atomic_add(&cursor[key], 1);
   sorted[offsets[key] + pos] = val;
   for (uint32_t v = 1; v < nviews; v++)
@@ -214,6 +216,36 @@ ZKB_HDN inline void msm_accum2_body(uint32_t L, uint32_t T, const uint32_t* key,
   }
   okey[2 * (size_t)t] = k0;
   okey[2 * (size_t)t + 1] = k1;
+}
+
+// ---- window table: table[w * n + i] = 2^(c w) * P_i (affine), one thread per point ------------------
+// The W-1 multiples are normalised with one shared inversion (Montgomery's trick) per point.
+template <class F, int MAXW>
+ZKB_HDN inline void msm_table_body(const Affine<F>* pts, Affine<F>* table, uint32_t n, uint32_t c, uint32_t W, uint32_t i) {
+  if (i >= n) return;
+  Affine<F> p = pts[i];
+  table[i] = p;
+  if (p.is_inf()) {
+    for (uint32_t w = 1; w < W; w++) table[(size_t)w * n + i] = Affine<F>::inf();
+    return;
+  }
+  XYZZ<F> cur = XYZZ<F>::from_affine(p);
+  XYZZ<F> mult[MAXW];
+  F pref[MAXW];
+  F run = F::one();
+  for (uint32_t w = 1; w < W; w++) {
+    for (uint32_t d = 0; d < c; d++) cur = XYZZ<F>::dbl_ni(cur);
+    mult[w] = cur;
+    pref[w] = run;                                   // product of the denominators before w
+    run = F::mul_ni(run, F::mul_ni(cur.zz, cur.zzz));  // a prime-order point never doubles to infinity
+  }
+  F inv = F::inv(run);
+  for (uint32_t w = W; w-- > 1;) {
+    F dinv = F::mul_ni(inv, pref[w]);                // 1 / (zz zzz)
+    inv = F::mul_ni(inv, F::mul_ni(mult[w].zz, mult[w].zzz));
+    F zzi = F::mul_ni(dinv, mult[w].zzz), zzzi = F::mul_ni(dinv, mult[w].zz);
+    table[(size_t)w * n + i] = Affine<F>{F::mul_ni(mult[w].x, zzi), F::mul_ni(mult[w].y, zzzi)};
+  }
 }
 
 // ---- bucket tree: per window sum_j (j+1) * bucket[j] via (A, Wt) pairs --------------------------
