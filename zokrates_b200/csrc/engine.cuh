@@ -53,6 +53,16 @@ struct StageTimer {
     open.pop_back();
     ZKB_CUDA(cudaEventRecord(evs[i].b, st.s));
   }
+  // spans on other streams (tails): begin_on returns a handle for end_on
+  size_t begin_on(Stream s, const char* name) {
+    Ev e{name, nullptr, nullptr};
+    ZKB_CUDA(cudaEventCreate(&e.a));
+    ZKB_CUDA(cudaEventCreate(&e.b));
+    ZKB_CUDA(cudaEventRecord(e.a, s.s));
+    evs.push_back(e);
+    return evs.size() - 1;
+  }
+  void end_on(Stream s, size_t i) { ZKB_CUDA(cudaEventRecord(evs[i].b, s.s)); }
   void collect(std::vector<std::pair<const char*, double>>& out) {
     out.clear();
     for (auto& e : evs) {
@@ -70,6 +80,8 @@ struct StageTimer {
   explicit StageTimer(Stream) {}
   void begin(const char*) {}
   void end() {}
+  size_t begin_on(Stream, const char*) { return 0; }
+  void end_on(Stream, size_t) {}
   void collect(std::vector<std::pair<const char*, double>>& out) { out.clear(); }
 #endif
 };
@@ -379,6 +391,7 @@ class Engine : public EngineBase {
     DevBuf<Fr> val[3];
     DevBuf<Fr> z_canon, z_mont, a, b, c, h;
     bool has_z = false;
+    bool sparse_z = false;  // most assignment values are tiny (bits): the z MSMs are cheap, prefer the shallow per-window trees
     // host copies kept for setup (CSC transposition) — small relative to the device data
     std::vector<uint32_t> h_rowptr[3], h_col[3];
   };
@@ -436,6 +449,7 @@ class Engine : public EngineBase {
     h2d(st_, r.z_canon.p, z, r.m * FRB);
     stream_sync(st_);
     r.has_z = true;
+    r.sparse_z = assignment_is_sparse(z, r.m);
   }
 
   // h (canonical, natural order) = witness_map(z)   [device-resident]
@@ -587,11 +601,12 @@ class Engine : public EngineBase {
   // a few thousand threads doing ~20 dependent point additions per level, so it runs on a high-priority
   // stream underneath the next MSM's accumulation.
   template <class F>
-  void msm_tail(const MsmPlan& pl, MsmWs& ws, XYZZ<F>* win_out /* 2 W entries */) {
+  void msm_tail(const MsmPlan& pl, MsmWs& ws, XYZZ<F>* win_out /* 2 W entries */, StageTimer* tm = nullptr, const char* tail_name = nullptr) {
     typedef XYZZ<F> X;
     if (pl.sh.n == 0) return;
     Stream ts = tail_stream(ws);
     ws.acc_done.wait(ts);
+    size_t span = (tm && tail_name) ? tm->begin_on(ts, tail_name) : 0;
     const uint32_t W = pl.sh.pre ? 1 : pl.sh.W, B = pl.sh.B, T2 = pl.T2, nt1 = pl.nt1;
     X* buckets = (X*)ws.buckets.p;
     uint32_t L = 2 * nt1;
@@ -624,14 +639,15 @@ class Engine : public EngineBase {
     // window sums (A_w, Wt_w) -> caller's slot; the 2^(c w) Horner runs on the host (see fp64.cuh)
     d2d(ts, win_out, inA, (size_t)W * sizeof(X));
     d2d(ts, win_out + W, inWt, (size_t)W * sizeof(X));
+    if (tm && tail_name) tm->end_on(ts, span);
     ws.tail_done.record(ts);
   }
 
   template <class F>
   void msm_exec(const MsmPlan& pl, const Affine<F>* pts, XYZZ<F>* win_out, MsmWs& ws, StageTimer* tm = nullptr,
-                const char* accum_name = nullptr, uint32_t view = 0) {
+                const char* accum_name = nullptr, uint32_t view = 0, const char* tail_name = nullptr) {
     msm_accumulate<F>(pl, pts, ws, tm, accum_name, view);
-    msm_tail<F>(pl, ws, win_out);
+    msm_tail<F>(pl, ws, win_out, tm, tail_name);
   }
 
   // result = sum_w 2^(c w) (A_w + Wt_w) on the host
@@ -830,6 +846,15 @@ class Engine : public EngineBase {
   };
   static_assert(sizeof(HostPartial) == sizeof(Partial), "partial layout");
 
+  // sample the assignment: a witness dominated by 0/1 values (hash circuits) makes the z MSMs nearly free, and the
+  // proof time is then set by the reduction tails — the windows mode (16 x 2^15 buckets) has the shallower tree.
+  static bool assignment_is_sparse(const uint64_t* z, uint64_t m) {
+    const uint64_t step = m > 4096 ? m / 4096 : 1;
+    uint64_t small = 0, cnt = 0;
+    for (uint64_t i = 0; i < m; i += step, cnt++) small += (z[4 * i + 1] | z[4 * i + 2] | z[4 * i + 3]) == 0;
+    return cnt && small * 2 > cnt;
+  }
+
   void prove_partial(uint64_t pkh, uint64_t rh, const uint64_t* z, uint8_t* partial_out) override {
     Pk& pk = get_pk(pkh);
     R1cs& r = get_r1cs(rh);
@@ -842,6 +867,7 @@ class Engine : public EngineBase {
       h2d(st_, r.z_canon.p, z, r.m * FRB);
       tm.end();
       r.has_z = true;
+      r.sparse_z = assignment_is_sparse(z, r.m);
     } else if (!r.has_z) {
       throw Error(ZKB_E_ARG, "no resident assignment");
     }
@@ -872,16 +898,16 @@ class Engine : public EngineBase {
       ev_h_ready_.record(st_);
     }
     tm.begin("msm_plan_z");
-    plan_build(plan_z_, r.z_canon.p + 1 + pk.lo, pk.hi - pk.lo, 3, pk.skip.p, pk.pre_cz);
+    plan_build(plan_z_, r.z_canon.p + 1 + pk.lo, pk.hi - pk.lo, 3, pk.skip.p, r.sparse_z ? 0 : pk.pre_cz);
     tm.end();
-    msm_exec<Fq2>(plan_z_, pk.b2.p, w_b2, ws_[4], &tm, "accum1_g2_b2", 2);
-    msm_exec<Fq>(plan_z_, pk.l.p, w_l, ws_[1], &tm, "accum1_g1_l", 0);
-    msm_exec<Fq>(plan_z_, pk.a.p, w_a, ws_[2], &tm, "accum1_g1_a", 1);
-    msm_exec<Fq>(plan_z_, pk.b1.p, w_b1, ws_[3], &tm, "accum1_g1_b1", 2);
+    msm_exec<Fq2>(plan_z_, pk.b2.p, w_b2, ws_[4], &tm, "accum1_g2_b2", 2, "tail_g2_b2");
+    msm_exec<Fq>(plan_z_, pk.l.p, w_l, ws_[1], &tm, "accum1_g1_l", 0, "tail_g1_l");
+    msm_exec<Fq>(plan_z_, pk.a.p, w_a, ws_[2], &tm, "accum1_g1_a", 1, "tail_g1_a");
+    msm_exec<Fq>(plan_z_, pk.b1.p, w_b1, ws_[3], &tm, "accum1_g1_b1", 2, "tail_g1_b1");
     tm.begin("wait_h");
     ev_h_ready_.wait(st_);
     tm.end();
-    msm_exec<Fq>(plan_h_, pk.h.p, w_h, ws_[0], &tm, "accum1_g1_h", 0);
+    msm_exec<Fq>(plan_h_, pk.h.p, w_h, ws_[0], &tm, "accum1_g1_h", 0, "tail_g1_h");
     tm.begin("tails_wait");
     for (int k = 0; k < 5; k++) ws_[k].tail_done.wait(st_);
     tm.end();

@@ -139,7 +139,19 @@ ZKB_HDN inline void msm_accum1_body(uint32_t nbuckets, uint32_t T, const uint32_
     XYZZ<F> acc = XYZZ<F>::identity();
     // ONE flat loop over the chunk: the bucket change is a short predicated block, so every lane of the
     // warp meets at the same mixed addition each iteration (no nested-loop divergence).
+    // software pipeline: the index (and, when registers allow, the point) of entry p+1 is fetched before the
+    // mixed addition of entry p, so the dependent gather sorted[p] -> points[.] hides behind ~2500 instructions
+    constexpr bool PREFETCH_POINT = sizeof(Affine<F>) <= 64;
+    uint32_t e = sorted[pos];
+    Affine<F> q;
+    if (PREFETCH_POINT) q = points[e & ~MSM_NEG];
     for (uint32_t p = pos; p < end; p++) {
+      uint32_t e_next = 0;
+      Affine<F> q_next;
+      if (p + 1 < end) {
+        e_next = sorted[p + 1];
+        if (PREFETCH_POINT) q_next = points[e_next & ~MSM_NEG];
+      }
       if (p == bend) {
         if (bstart >= cstart) buckets[b] = acc;            // complete (it also ends inside the chunk)
         else { k0 = b; pval[2 * (size_t)t] = acc; }        // began in the previous chunk
@@ -149,10 +161,11 @@ ZKB_HDN inline void msm_accum1_body(uint32_t nbuckets, uint32_t T, const uint32_
         bend = offsets[b + 1];
         acc = XYZZ<F>::identity();
       }
-      uint32_t e = sorted[p];
-      Affine<F> q = points[e & ~MSM_NEG];
+      if (!PREFETCH_POINT) q = points[e & ~MSM_NEG];
       if (e & MSM_NEG) q.y = F::neg(q.y);
       acc = XYZZ<F>::madd(acc, q);
+      e = e_next;
+      if (PREFETCH_POINT) q = q_next;
     }
     if (bstart >= cstart && bend <= end) buckets[b] = acc;
     else if (bstart < cstart) { k0 = b; pval[2 * (size_t)t] = acc; }
