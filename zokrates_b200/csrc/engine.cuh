@@ -964,13 +964,18 @@ class Engine : public EngineBase {
     HG1X ga = HG1X::madd(HG1X::madd(HG1X::add(fm.rd, sum.a), pk.h_fixed1[3]), pk.h_fixed1[0]);
     HG1X gb1 = HG1X::madd(HG1X::madd(HG1X::add(fm.sd, sum.b1), pk.h_fixed1[4]), pk.h_fixed1[1]);
     HG2X gb2 = HG2X::madd(HG2X::madd(HG2X::add(fm.sd2, sum.b2), pk.h_fixed2[2]), pk.h_fixed2[0]);
-    // C = s A + r B1 - r s d1 + L + H
-    HG1X gc = HG1X::add(HG1X::mul_xyzz(ga, s, 8), HG1X::mul_xyzz(gb1, r, 8));
+    // C = s A + r B1 - r s d1 + L + H.  The two variable-base multiplications and the G2 normalisation are
+    // independent: three host threads.
+    auto fut_u2 = std::async(std::launch::async, [&gb1, r] { return HG1X::mul_xyzz(gb1, r, 8); });
+    auto fut_pb = std::async(std::launch::async, [&gb2] { return HG2X::to_affine(gb2); });
+    HG1X gc = HG1X::mul_xyzz(ga, s, 8);
+    HG1A pa = HG1X::to_affine(ga);
+    gc = HG1X::add(gc, fut_u2.get());
     gc = HG1X::add(gc, HG1X::neg(fm.rsd));
     gc = HG1X::add(gc, sum.l);
     gc = HG1X::add(gc, sum.h);
-    HG1A pa = HG1X::to_affine(ga), pc = HG1X::to_affine(gc);
-    HG2A pb = HG2X::to_affine(gb2);
+    HG1A pc = HG1X::to_affine(gc);
+    HG2A pb = fut_pb.get();
     auto put = [&](size_t slot, const HFq& v) { HFq c = HFq::from_mont(v); memcpy(proof_out + slot * FQB, c.v, FQB); };
     put(0, pa.x); put(1, pa.y); put(2, pb.x.c0); put(3, pb.x.c1); put(4, pb.y.c0); put(5, pb.y.c1); put(6, pc.x); put(7, pc.y);
   }
