@@ -29,7 +29,7 @@ struct k_fr_convert; struct k_spmv; struct k_ntt_dif; struct k_ntt_dit; struct k
 struct k_ntt_table; struct k_qap_pointwise; struct k_msm_digits; struct k_msm_scatter; struct k_msm_accum1;
 struct k_msm_accum2; struct k_msm_tree; struct k_msm_horner; struct k_pk_convert; struct k_final_a; struct k_final_b;
 struct k_final_c; struct k_final_d; struct k_point_out; struct k_field_op; struct k_setup_scalars; struct k_fixed_base;
-struct k_to_affine; struct k_copy; struct k_msm_table;
+struct k_to_affine; struct k_copy; struct k_msm_table; struct k_msm_tree_coop;
 
 // ---------------------------------------------------------------------------------------------
 // stage timer: CUDA events on the engine stream (no-op in the host emulation)
@@ -541,7 +541,7 @@ class Engine : public EngineBase {
 
   // per-MSM scratch so that the latency-bound tails of different MSMs can overlap
   struct MsmWs {
-    DevBuf<uint8_t> buckets, val[2], tree[4];
+    DevBuf<uint8_t> buckets, val[2], tree[4], coop[4];
     DevBuf<uint32_t> key[2];
     Stream tail;          // high-priority side stream for accum2 / tree
     Event acc_done, tail_done;
@@ -625,15 +625,35 @@ class Engine : public EngineBase {
     size_t first = (size_t)W * ((B + 7) / 8);
     for (int k = 0; k < 4; k++) ws.tree[k].ensure(first * sizeof(X));
     const X* inA = buckets; const X* inWt = nullptr;
-    uint32_t cnt = B, lvl = 0;
+    uint32_t cnt = B, lvl = 0, bits_done = 0;
     int pp = 0;
+    static const int coop = getenv("ZKB_TREE_COOP") ? atoi(getenv("ZKB_TREE_COOP")) : 1;
     while (cnt > 1) {
-      uint32_t cnt_out = (cnt + 7) / 8;
       X* oA = (X*)ws.tree[pp].p; X* oW = (X*)ws.tree[pp + 1].p;
       const X* iA = inA; const X* iW = inWt;
-      uint32_t ci = cnt, lv = lvl;
-      launch<k_msm_tree>(ts, (size_t)W * cnt_out, ZKB_LAMBDA(size_t t) { msm_tree_body<F>(W, ci, lr, lv, iA, iW, oA, oW, (uint32_t)t); });
-      inA = oA; inWt = oW; cnt = cnt_out; lvl++;
+      uint32_t ci = cnt;
+      if (lvl == 0 || !coop) {
+        // leaves: many nodes, sequential fan-in 8 per thread (throughput-bound)
+        uint32_t cnt_out = (cnt + 7) / 8;
+        uint32_t lv = lvl;
+        launch<k_msm_tree>(ts, (size_t)W * cnt_out, ZKB_LAMBDA(size_t t) { msm_tree_body<F>(W, ci, lr, lv, iA, iW, oA, oW, (uint32_t)t); });
+        cnt = cnt_out; bits_done += lr;
+      } else {
+        // upper levels: few nodes, 16 threads per node with log-step scan / reduction (latency-bound)
+        const uint32_t f = 4, Fn = 16;
+        uint32_t cnt_out = (cnt + Fn - 1) / Fn;
+        size_t slots = (size_t)W * cnt_out * Fn;
+        constexpr int CB = 128;
+        size_t nblocks = (slots + CB - 1) / CB;
+        for (int k = 0; k < 4; k++) ws.coop[k].ensure(nblocks * CB * sizeof(X));
+        X* s0 = (X*)ws.coop[0].p; X* s1 = (X*)ws.coop[1].p; X* vv = (X*)ws.coop[2].p; X* rr = (X*)ws.coop[3].p;
+        uint32_t shift = bits_done;
+        launch_phased<k_msm_tree_coop, CB>(ts, nblocks, 2 * f + 2, ZKB_LAMBDA(uint32_t b, uint32_t t, uint32_t ph) {
+          msm_tree_coop_body<F>(W, ci, f, shift, iA, iW, oA, oW, s0, s1, vv, rr, CB, b, t, ph);
+        });
+        cnt = cnt_out; bits_done += f;
+      }
+      inA = oA; inWt = oW; lvl++;
       pp ^= 2;
     }
     // window sums (A_w, Wt_w) -> caller's slot; the 2^(c w) Horner runs on the host (see fp64.cuh)

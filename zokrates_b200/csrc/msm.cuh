@@ -285,6 +285,64 @@ ZKB_HDN inline void msm_tree_body(uint32_t W, uint32_t cnt_in, uint32_t lr, uint
   outWt[(size_t)w * cnt_out + k] = XYZZ<F>::add(wsum, wrel);
 }
 
+// ---- cooperative tree level: F = 2^f children per node, F threads per node -----------------------
+// The sequential node above costs 3 F dependent additions; here the suffix sums are a log-step scan and
+// the two totals a log-step reduction: 3 f dependent additions per level (f bits of the bucket index).
+// Scratch (global, per thread slot): S0, S1 (scan ping-pong), V (weights), R (reduction).
+// Phases: 0 load | 1..f scan | f+1..2f reduce | 2f+1 finish.   Node n of window w <-> global node id w*cnt_out+n.
+template <class F>
+ZKB_HDN inline void msm_tree_coop_body(uint32_t W, uint32_t cnt_in, uint32_t f, uint32_t shift, const XYZZ<F>* inA,
+                                       const XYZZ<F>* inWt, XYZZ<F>* outA, XYZZ<F>* outWt, XYZZ<F>* S0, XYZZ<F>* S1, XYZZ<F>* V,
+                                       XYZZ<F>* R, uint32_t block_threads, uint32_t block, uint32_t thread, uint32_t phase) {
+  typedef XYZZ<F> X;
+  const uint32_t Fn = 1u << f;
+  const uint32_t cnt_out = (cnt_in + Fn - 1) >> f;
+  const size_t slot = (size_t)block * block_threads + thread;   // global thread slot
+  const size_t node = slot >> f;
+  const uint32_t i = (uint32_t)(slot & (Fn - 1));                // child index inside the node
+  if (node >= (size_t)W * cnt_out) return;
+  const uint32_t w = (uint32_t)(node / cnt_out), k = (uint32_t)(node % cnt_out);
+  const size_t base = slot - i;                                  // slot of child 0 of this node
+  if (phase == 0) {
+    const uint32_t child = (k << f) + i;
+    if (child < cnt_in) { S0[slot] = inA[(size_t)w * cnt_in + child]; V[slot] = inWt[(size_t)w * cnt_in + child]; }
+    else { S0[slot] = X::identity(); V[slot] = X::identity(); }
+    return;
+  }
+  if (phase <= f) {                                              // inclusive suffix scan, step 2^(phase-1)
+    const uint32_t step = 1u << (phase - 1);
+    const X* src = (phase & 1) ? S0 : S1;
+    X* dst = (phase & 1) ? S1 : S0;
+    X v = src[slot];
+    if (i + step < Fn) v = X::add(v, src[slot + step]);
+    dst[slot] = v;
+    return;
+  }
+  const X* Sfin = (f & 1) ? S1 : S0;                             // result of the last scan phase
+  if (phase <= 2 * f) {                                          // tree reduction, step 2^(2f - phase)
+    const uint32_t step = 1u << (2 * f - phase);
+    if (i < step) {
+      X a, b;
+      if (phase == f + 1) {                                      // first step reads the scan result, dropping S[0]
+        a = i ? Sfin[slot] : X::identity();
+        b = Sfin[slot + step];
+      } else {
+        a = R[slot];
+        b = R[slot + step];
+      }
+      R[slot] = X::add(a, b);
+      V[slot] = X::add(V[slot], V[slot + step]);
+    }
+    return;
+  }
+  if (i == 0) {                                                  // finish: A = S[0], Wt = sum Wt_i + 2^shift * sum_i i A_i
+    X wrel = (f == 0) ? X::identity() : R[base];
+    for (uint32_t d = 0; d < shift; d++) wrel = X::dbl(wrel);
+    outA[node] = Sfin[base];
+    outWt[node] = X::add(V[base], wrel);
+  }
+}
+
 // ---- window combine: result = sum_w 2^(c w) (Wt_w + A_w)  (single thread) ------------------------
 template <class F>
 ZKB_HDN inline void msm_horner_body(uint32_t W, uint32_t c, const XYZZ<F>* A, const XYZZ<F>* Wt, XYZZ<F>* out) {

@@ -64,6 +64,24 @@ inline void launch(Stream st, size_t n, Fn fn) {
   ZKB_CUDA(cudaGetLastError());
 }
 
+// Block-cooperative kernels: `nphases` steps separated by __syncthreads(); threads of a block exchange data
+// through (L1-coherent) global scratch.  fn(block, thread, phase).  The host emulation runs phase by phase.
+template <class Tag, int BLOCK, class Fn>
+__global__ void __launch_bounds__(BLOCK) zkb_phased_kernel(uint32_t nphases, Fn fn) {
+  for (uint32_t ph = 0; ph < nphases; ph++) {
+    fn((uint32_t)blockIdx.x, (uint32_t)threadIdx.x, ph);
+    __syncthreads();
+  }
+}
+template <class Tag, int BLOCK, class Fn>
+inline void launch_phased(Stream st, size_t nblocks, uint32_t nphases, Fn fn) {
+  if (nblocks == 0) return;
+  launch_counter()++;
+  if (nblocks > 0x7fffffffull) throw Error(ZKB_E_ARG, "grid too large");
+  zkb_phased_kernel<Tag, BLOCK, Fn><<<(unsigned)nblocks, BLOCK, 0, st.s>>>(nphases, fn);
+  ZKB_CUDA(cudaGetLastError());
+}
+
 inline void* dev_alloc(size_t bytes) {
   void* p = nullptr;
   if (bytes == 0) bytes = 16;
@@ -126,6 +144,13 @@ template <class Tag, int BLOCK = 128, int MINB = 1, class Fn>
 inline void launch(Stream, size_t n, Fn fn) {
   if (n) launch_counter()++;
   for (size_t tid = 0; tid < n; tid++) fn(tid);
+}
+template <class Tag, int BLOCK, class Fn>
+inline void launch_phased(Stream, size_t nblocks, uint32_t nphases, Fn fn) {
+  if (nblocks) launch_counter()++;
+  for (size_t b = 0; b < nblocks; b++)
+    for (uint32_t ph = 0; ph < nphases; ph++)
+      for (uint32_t t = 0; t < (uint32_t)BLOCK; t++) fn((uint32_t)b, t, ph);
 }
 inline void* dev_alloc(size_t bytes) {
   void* p = malloc(bytes ? bytes : 16);
