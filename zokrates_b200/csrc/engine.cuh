@@ -180,6 +180,8 @@ struct MsmPlan {
   uint32_t T1 = 32, T2 = 32;
   uint32_t nt1 = 0;  // level-1 chunks
   uint32_t nviews = 1;
+  // filled by msm_tail: the GPU tree stops at `tree_cnt` nodes per window (each spanning 2^tree_bits buckets); the host finishes
+  mutable uint32_t tree_cnt = 1, tree_bits = 0;
   DevBuf<uint32_t> digits, counts, offsets, cursor, sorted, scan_tmp;
 };
 
@@ -522,7 +524,7 @@ class Engine : public EngineBase {
     if (T > 64) T = 64;
     T = (T + 1) & ~1ull;
     pl.T1 = (uint32_t)T;
-    pl.T2 = 32;
+    pl.T2 = 8;   // short chunks at the partial levels: fewer dependent additions per level
     pl.nt1 = (uint32_t)((total + pl.T1 - 1) / pl.T1);
     const uint32_t NB = pl.nbuckets;
     pl.digits.ensure(total); pl.sorted.ensure(total * nviews);
@@ -628,7 +630,8 @@ class Engine : public EngineBase {
     uint32_t cnt = B, lvl = 0, bits_done = 0;
     int pp = 0;
     static const int coop = getenv("ZKB_TREE_COOP") ? atoi(getenv("ZKB_TREE_COOP")) : 1;
-    while (cnt > 1) {
+    // the last few hundred nodes are cheaper on a host core (0.5 us per addition instead of ~8 us of dependent latency)
+    while ((size_t)W * cnt > HOST_TREE_NODES) {
       X* oA = (X*)ws.tree[pp].p; X* oW = (X*)ws.tree[pp + 1].p;
       const X* iA = inA; const X* iW = inWt;
       uint32_t ci = cnt;
@@ -656,9 +659,16 @@ class Engine : public EngineBase {
       inA = oA; inWt = oW; lvl++;
       pp ^= 2;
     }
-    // window sums (A_w, Wt_w) -> caller's slot; the 2^(c w) Horner runs on the host (see fp64.cuh)
-    d2d(ts, win_out, inA, (size_t)W * sizeof(X));
-    d2d(ts, win_out + W, inWt, (size_t)W * sizeof(X));
+    // remaining nodes (A, Wt) -> caller's slot; the host finishes the tree and the 2^(c w) Horner (fp64.cuh)
+    pl.tree_cnt = cnt; pl.tree_bits = bits_done;
+    const size_t nodes = (size_t)W * cnt;
+    if (lvl == 0) {  // tiny bucket set: nothing ran on the GPU, the nodes are the buckets themselves (Wt = 0)
+      d2d(ts, win_out, buckets, nodes * sizeof(X));
+      dev_zero(ts, win_out + nodes, nodes * sizeof(X));
+    } else {
+      d2d(ts, win_out, inA, nodes * sizeof(X));
+      d2d(ts, win_out + nodes, inWt, nodes * sizeof(X));
+    }
     if (tm && tail_name) tm->end_on(ts, span);
     ws.tail_done.record(ts);
   }
@@ -670,13 +680,26 @@ class Engine : public EngineBase {
     msm_tail<F>(pl, ws, win_out, tm, tail_name);
   }
 
-  // result = sum_w 2^(c w) (A_w + Wt_w) on the host
+  // Host finish of one MSM: per window, sum_k [Wt_k + 2^bits * k * A_k] + sum_k A_k over the `cnt` remaining tree
+  // nodes (running sums), then result = sum_w 2^(c w) S_w.
+  static constexpr size_t HOST_TREE_NODES = 256;
   template <class HX>
-  static HX host_horner(const HX* win, uint32_t W, uint32_t c) {
+  static HX host_finish(const HX* nodes, const MsmPlan& pl) {
+    const uint32_t W = pl.sh.pre ? 1 : pl.sh.W, cnt = pl.tree_cnt, bits = pl.tree_bits, c = pl.sh.c;
+    const HX* A = nodes;
+    const HX* Wt = nodes + (size_t)W * cnt;
     HX acc = HX::identity();
     for (uint32_t w = W; w-- > 0;) {
       for (uint32_t d = 0; d < c; d++) acc = HX::dbl(acc);
-      acc = HX::add(acc, HX::add(win[w], win[W + w]));
+      HX run = HX::identity(), wrel = HX::identity(), wsum = HX::identity();
+      for (uint32_t k = cnt; k-- > 0;) {
+        run = HX::add(run, A[(size_t)w * cnt + k]);
+        if (k > 0) wrel = HX::add(wrel, run);
+        wsum = HX::add(wsum, Wt[(size_t)w * cnt + k]);
+      }
+      for (uint32_t d = 0; d < bits; d++) wrel = HX::dbl(wrel);
+      // bucket j holds weight j + 1: sum (j + 1) B_j = Wt + (relative weights) + A
+      acc = HX::add(acc, HX::add(HX::add(wsum, wrel), run));
     }
     return acc;
   }
@@ -858,7 +881,7 @@ class Engine : public EngineBase {
   MsmPlan plan_z_, plan_h_;
   DevBuf<Fr> scratch_a_, scratch_b_;
   DevBuf<uint8_t> d_win_;
-  static constexpr uint32_t MAXW = 72;  // windows per MSM never exceed ceil(256 / 4)
+  static constexpr uint32_t MAXW = 256;  // result slot: 2 x (at most HOST_TREE_NODES tree nodes per MSM)
 
   struct HostPartial {  // same layout as Partial
     HG1X h, l, a, b1;
@@ -943,12 +966,18 @@ class Engine : public EngineBase {
       for (auto& e : t2) timings.push_back(e);
     }
     HostPartial hp;
+    // five independent host reductions (a few hundred point additions each): one thread per MSM
     auto hor1 = [&](size_t k, const MsmPlan& pl) {
-      return pl.sh.n ? host_horner<HG1X>((const HG1X*)(hw.data() + k * slot1), pl.sh.pre ? 1 : pl.sh.W, pl.sh.c) : HG1X::identity();
+      return pl.sh.n ? host_finish<HG1X>((const HG1X*)(hw.data() + k * slot1), pl) : HG1X::identity();
     };
-    hp.h = hor1(0, plan_h_); hp.l = hor1(1, plan_z_); hp.a = hor1(2, plan_z_); hp.b1 = hor1(3, plan_z_);
-    hp.b2 = plan_z_.sh.n ? host_horner<HG2X>((const HG2X*)(hw.data() + 4 * slot1), plan_z_.sh.pre ? 1 : plan_z_.sh.W, plan_z_.sh.c)
-                         : HG2X::identity();
+    auto f_b2 = std::async(std::launch::async, [&] {
+      return plan_z_.sh.n ? host_finish<HG2X>((const HG2X*)(hw.data() + 4 * slot1), plan_z_) : HG2X::identity();
+    });
+    auto f_h = std::async(std::launch::async, [&] { return hor1(0, plan_h_); });
+    auto f_l = std::async(std::launch::async, [&] { return hor1(1, plan_z_); });
+    auto f_a = std::async(std::launch::async, [&] { return hor1(2, plan_z_); });
+    hp.b1 = hor1(3, plan_z_);
+    hp.h = f_h.get(); hp.l = f_l.get(); hp.a = f_a.get(); hp.b2 = f_b2.get();
     memcpy(partial_out, &hp, sizeof hp);
   }
 
@@ -1054,7 +1083,7 @@ class Engine : public EngineBase {
     d2h(st_, hw.data(), d_win_.p, hw.size());
     stream_sync(st_);
     tm.collect(timings);
-    HX res = n ? host_horner<HX>((const HX*)hw.data(), plan_misc_.sh.W, plan_misc_.sh.c) : HX::identity();
+    HX res = n ? host_finish<HX>((const HX*)hw.data(), plan_misc_) : HX::identity();
     HA a = HX::to_affine(res);
     const size_t words = sizeof(A) / 4;
     uint32_t* o = (uint32_t*)out;
