@@ -629,7 +629,9 @@ class Engine : public EngineBase {
     const X* inA = buckets; const X* inWt = nullptr;
     uint32_t cnt = B, lvl = 0, bits_done = 0;
     int pp = 0;
-    static const int coop = getenv("ZKB_TREE_COOP") ? atoi(getenv("ZKB_TREE_COOP")) : 1;
+    // cooperative upper levels shorten the dependent chain 3x but add work that competes with the accumulate kernels:
+    // measured neutral-to-negative on B200 (profiles/r01_tuning_log.md), so off by default
+    static const int coop = getenv("ZKB_TREE_COOP") ? atoi(getenv("ZKB_TREE_COOP")) : 0;
     // the last few hundred nodes are cheaper on a host core (0.5 us per addition instead of ~8 us of dependent latency)
     while ((size_t)W * cnt > HOST_TREE_NODES) {
       X* oA = (X*)ws.tree[pp].p; X* oW = (X*)ws.tree[pp + 1].p;
@@ -692,10 +694,42 @@ class Engine : public EngineBase {
     for (uint32_t w = W; w-- > 0;) {
       for (uint32_t d = 0; d < c; d++) acc = HX::dbl(acc);
       HX run = HX::identity(), wrel = HX::identity(), wsum = HX::identity();
-      for (uint32_t k = cnt; k-- > 0;) {
-        run = HX::add(run, A[(size_t)w * cnt + k]);
-        if (k > 0) wrel = HX::add(wrel, run);
-        wsum = HX::add(wsum, Wt[(size_t)w * cnt + k]);
+      const uint32_t SEG = 4;
+      if (cnt >= 64 && cnt % SEG == 0 && ((cnt / SEG) & (cnt / SEG - 1)) == 0) {
+        // four host threads, one quarter of the nodes each; quarter q has base q * cnt/4:
+        // sum k A_k = sum_q [ local + (q * cnt/4) * run_q ]
+        const uint32_t len = cnt / SEG;
+        HX r_[SEG], w_[SEG], s_[SEG];
+        auto part = [&](uint32_t q) {
+          HX rr = HX::identity(), ww = HX::identity(), ss = HX::identity();
+          for (uint32_t k = len; k-- > 0;) {
+            size_t idx = (size_t)w * cnt + q * len + k;
+            rr = HX::add(rr, A[idx]);
+            if (k > 0) ww = HX::add(ww, rr);
+            ss = HX::add(ss, Wt[idx]);
+          }
+          r_[q] = rr; w_[q] = ww; s_[q] = ss;
+        };
+        std::future<void> fut[SEG - 1];
+        for (uint32_t q = 1; q < SEG; q++) fut[q - 1] = std::async(std::launch::async, part, q);
+        part(0);
+        for (uint32_t q = 1; q < SEG; q++) fut[q - 1].get();
+        HX qsum = HX::identity(), qrun = HX::identity();       // sum_q q * run_q by running sums
+        for (uint32_t q = SEG; q-- > 0;) {
+          qrun = HX::add(qrun, r_[q]);
+          if (q > 0) qsum = HX::add(qsum, qrun);
+          wrel = HX::add(wrel, w_[q]);
+          wsum = HX::add(wsum, s_[q]);
+        }
+        run = qrun;
+        for (uint32_t t = len; t > 1; t >>= 1) qsum = HX::dbl(qsum);   // times len (a power of two: cnt is)
+        wrel = HX::add(wrel, qsum);
+      } else {
+        for (uint32_t k = cnt; k-- > 0;) {
+          run = HX::add(run, A[(size_t)w * cnt + k]);
+          if (k > 0) wrel = HX::add(wrel, run);
+          wsum = HX::add(wsum, Wt[(size_t)w * cnt + k]);
+        }
       }
       for (uint32_t d = 0; d < bits; d++) wrel = HX::dbl(wrel);
       // bucket j holds weight j + 1: sum (j + 1) B_j = Wt + (relative weights) + A
