@@ -271,9 +271,17 @@ def main():
         modmul_peak = ctx.peak_probe(1, 4000)
         imad_peak = ctx.peak_probe(0, 40000)
         alg_bytes = n_pairs * 96.0                       # 32 B scalar + 64 B affine point per pair
+        traffic = None                                   # DRAM bytes per launch from the committed ncu --set full capture
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["k_msm_accum1<Fq> (h_query MSM)"]
+            traffic = tr["dram_bytes"] / world
+        except (OSError, KeyError, ValueError):
+            pass
         alg_muls = n_pairs * 16 * 10.0                   # canonical: W = 16 windows x 10 Fq-mul per mixed add
         roofline = {"kernel": "k_msm_accum1<Fq> (h_query MSM)", "bound": "hbm", "achieved": alg_bytes / (acc_ms * 1e-3) / 1e9,
-                    "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / (acc_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / (acc_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic,
+                    "traffic_note": "ncu dram__bytes_read+write of this kernel (profiles/r01_ncu_accum1_summary.md): the gathers go to 5 GB of "
+                                    "HBM-resident window tables 2^(cw)P, a deliberate bytes-for-multiplications trade (19% fewer mixed additions)",
                     "peak_source": hbm_src, "avg_launch_ms": acc_ms,
                     "note": "the kernel is integer-multiply bound, not HBM bound (230 MAD/B): see roofline_modmul"}
         roofline_mm = {"kernel": "k_msm_accum1<Fq> (h_query MSM)", "bound": "int32-mad", "achieved": alg_muls / (acc_ms * 1e-3),

@@ -630,20 +630,27 @@ class Engine : public EngineBase {
     uint32_t cnt = B, lvl = 0, bits_done = 0;
     int pp = 0;
     // cooperative upper levels shorten the dependent chain 3x but add work that competes with the accumulate kernels:
-    // measured neutral-to-negative on B200 (profiles/r01_tuning_log.md), so off by default
+    // measured neutral-to-negative on B200 (profiles/r01_tuning_log.md): compiled only with -DZKB_TREE_COOP_BUILD
     static const int coop = getenv("ZKB_TREE_COOP") ? atoi(getenv("ZKB_TREE_COOP")) : 0;
     // the last few hundred nodes are cheaper on a host core (0.5 us per addition instead of ~8 us of dependent latency)
     while ((size_t)W * cnt > HOST_TREE_NODES) {
       X* oA = (X*)ws.tree[pp].p; X* oW = (X*)ws.tree[pp + 1].p;
       const X* iA = inA; const X* iW = inWt;
       uint32_t ci = cnt;
+#if !defined(ZKB_TREE_COOP_BUILD)
+      (void)coop;
+      {
+#else
       if (lvl == 0 || !coop) {
+#endif
         // leaves: many nodes, sequential fan-in 8 per thread (throughput-bound)
         uint32_t cnt_out = (cnt + 7) / 8;
         uint32_t lv = lvl;
         launch<k_msm_tree>(ts, (size_t)W * cnt_out, ZKB_LAMBDA(size_t t) { msm_tree_body<F>(W, ci, lr, lv, iA, iW, oA, oW, (uint32_t)t); });
         cnt = cnt_out; bits_done += lr;
-      } else {
+      }
+#if defined(ZKB_TREE_COOP_BUILD)
+      else {
         // upper levels: few nodes, 16 threads per node with log-step scan / reduction (latency-bound)
         const uint32_t f = 4, Fn = 16;
         uint32_t cnt_out = (cnt + Fn - 1) / Fn;
@@ -658,6 +665,7 @@ class Engine : public EngineBase {
         });
         cnt = cnt_out; bits_done += f;
       }
+#endif
       inA = oA; inWt = oW; lvl++;
       pp ^= 2;
     }
