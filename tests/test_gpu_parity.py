@@ -240,3 +240,9 @@ def test_error_paths(cc):
     with pytest.raises(ZkbError) as e:
         ctx.prove(12345, 67890, np.zeros((3, 4), dtype=np.uint64), 1, 2)
     assert e.value.code == 1
+
+
+@pytest.mark.parametrize("case", range(7))
+def test_reference_edge_programs(case, gpu_lib):
+    from tests.util import check_backend_roundtrip, reference_edge_programs
+    check_backend_roundtrip(None, *reference_edge_programs()[case])

@@ -158,3 +158,11 @@ def test_error_paths(cc):
     h2 = ctx.r1cs_load(r2.num_constraints, r2.num_instance, r2.num_witness, r2.matrices())
     with pytest.raises(ZkbError):     # key of another circuit
         ctx.prove(ctx.pk_load(pk), h2, np.zeros((r2.num_variables, 4), dtype=np.uint64), 1, 2)
+
+
+@pytest.mark.parametrize("case", range(7))
+def test_reference_edge_programs(case, emu_lib):
+    """empty / identity / public identity / no arguments / `+ one` / unordered variables / public output
+    (the program shapes of the reference's own backend tests)."""
+    from tests.util import check_backend_roundtrip, reference_edge_programs
+    check_backend_roundtrip(emu_lib, *reference_edge_programs()[case])

@@ -11,6 +11,7 @@
 #include <map>
 #include <memory>
 #include <vector>
+#include <chrono>
 #include <future>
 #include "fp64.cuh"
 #include "msm.cuh"
@@ -1008,6 +1009,7 @@ class Engine : public EngineBase {
       for (auto& e : t2) timings.push_back(e);
     }
     HostPartial hp;
+    const auto t_host0 = std::chrono::steady_clock::now();
     // five independent host reductions (a few hundred point additions each): one thread per MSM
     auto hor1 = [&](size_t k, const MsmPlan& pl) {
       return pl.sh.n ? host_finish<HG1X>((const HG1X*)(hw.data() + k * slot1), pl) : HG1X::identity();
@@ -1020,6 +1022,7 @@ class Engine : public EngineBase {
     auto f_a = std::async(std::launch::async, [&] { return hor1(2, plan_z_); });
     hp.b1 = hor1(3, plan_z_);
     hp.h = f_h.get(); hp.l = f_l.get(); hp.a = f_a.get(); hp.b2 = f_b2.get();
+    timings.push_back({"host_tree_finish", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count()});
     memcpy(partial_out, &hp, sizeof hp);
   }
 
@@ -1091,8 +1094,10 @@ class Engine : public EngineBase {
       fut.wait();
       throw;
     }
+    const auto t0 = std::chrono::steady_clock::now();
     FixedMults fm = fut.get();
     finalize_with(pk, fm, partial.data(), 1, (const uint32_t*)r, (const uint32_t*)s, proof_out);
+    timings.push_back({"host_final_combine", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()});
   }
 
   // ------------------------------------------------------------------------------ standalone MSM (tests / microbench)
