@@ -634,7 +634,9 @@ class Engine : public EngineBase {
     // measured neutral-to-negative on B200 (profiles/r01_tuning_log.md): compiled only with -DZKB_TREE_COOP_BUILD
     static const int coop = getenv("ZKB_TREE_COOP") ? atoi(getenv("ZKB_TREE_COOP")) : 0;
     // the last few hundred nodes are cheaper on a host core (0.5 us per addition instead of ~8 us of dependent latency)
-    while ((size_t)W * cnt > HOST_TREE_NODES) {
+    // (a G2 addition costs 1.3 us on the host, so the G2 tree goes further down on the GPU — its tail is not the last to finish)
+    const size_t host_nodes = sizeof(F) > sizeof(Fq) ? HOST_TREE_NODES / 8 : HOST_TREE_NODES;
+    while (cnt > 1 && (size_t)W * cnt > host_nodes) {
       X* oA = (X*)ws.tree[pp].p; X* oW = (X*)ws.tree[pp + 1].p;
       const X* iA = inA; const X* iW = inWt;
       uint32_t ci = cnt;
