@@ -89,7 +89,7 @@ def test_msm_g2(cc, n):
     assert ctx.msm(2, b"".join(ark.ser_g2(c, p) for p in pts), fr_array(sc)) == ark.ser_g2(c, G2.msm_naive(pts, sc))
 
 
-@pytest.mark.parametrize("shape", [(1, 1, 1), (5, 2, 1), (13, 0, 3), (30, 1, 2)], ids=str)
+@pytest.mark.parametrize("shape", [(1, 1, 1), (5, 2, 1), (13, 0, 3), (30, 1, 2), (100, 1, 2)], ids=str)
 def test_prove_through_backend_mirror(cc, shape, emu_lib):
     """`B200::generate_proof` (host mirror -> C ABI) equals the oracle's prover byte for byte, the
     trapdoor prediction, and verifies; setup output equals the oracle's proving key bytes."""

@@ -181,8 +181,6 @@ struct MsmPlan {
   uint32_t T1 = 32, T2 = 32;
   uint32_t nt1 = 0;  // level-1 chunks
   uint32_t nviews = 1;
-  // filled by msm_tail: the GPU tree stops at `tree_cnt` nodes per window (each spanning 2^tree_bits buckets); the host finishes
-  mutable uint32_t tree_cnt = 1, tree_bits = 0;
   DevBuf<uint32_t> digits, counts, offsets, cursor, sorted, scan_tmp;
 };
 
@@ -549,6 +547,8 @@ class Engine : public EngineBase {
     Stream tail;          // high-priority side stream for accum2 / tree
     Event acc_done, tail_done;
     bool has_stream = false;
+    // filled by msm_tail: the GPU tree stopped at `tree_cnt` nodes per window (each spanning 2^tree_bits buckets)
+    uint32_t tree_cnt = 1, tree_bits = 0;
   };
   static constexpr int NUM_WS = 6;   // h, l, a, b1, b2, misc
   MsmWs ws_[NUM_WS];
@@ -673,7 +673,7 @@ class Engine : public EngineBase {
       pp ^= 2;
     }
     // remaining nodes (A, Wt) -> caller's slot; the host finishes the tree and the 2^(c w) Horner (fp64.cuh)
-    pl.tree_cnt = cnt; pl.tree_bits = bits_done;
+    ws.tree_cnt = cnt; ws.tree_bits = bits_done;
     const size_t nodes = (size_t)W * cnt;
     if (lvl == 0) {  // tiny bucket set: nothing ran on the GPU, the nodes are the buckets themselves (Wt = 0)
       d2d(ts, win_out, buckets, nodes * sizeof(X));
@@ -697,8 +697,8 @@ class Engine : public EngineBase {
   // nodes (running sums), then result = sum_w 2^(c w) S_w.
   static constexpr size_t HOST_TREE_NODES = 256;
   template <class HX>
-  static HX host_finish(const HX* nodes, const MsmPlan& pl) {
-    const uint32_t W = pl.sh.pre ? 1 : pl.sh.W, cnt = pl.tree_cnt, bits = pl.tree_bits, c = pl.sh.c;
+  static HX host_finish(const HX* nodes, const MsmPlan& pl, const MsmWs& ws) {
+    const uint32_t W = pl.sh.pre ? 1 : pl.sh.W, cnt = ws.tree_cnt, bits = ws.tree_bits, c = pl.sh.c;
     const HX* A = nodes;
     const HX* Wt = nodes + (size_t)W * cnt;
     HX acc = HX::identity();
@@ -1014,10 +1014,10 @@ class Engine : public EngineBase {
     const auto t_host0 = std::chrono::steady_clock::now();
     // five independent host reductions (a few hundred point additions each): one thread per MSM
     auto hor1 = [&](size_t k, const MsmPlan& pl) {
-      return pl.sh.n ? host_finish<HG1X>((const HG1X*)(hw.data() + k * slot1), pl) : HG1X::identity();
+      return pl.sh.n ? host_finish<HG1X>((const HG1X*)(hw.data() + k * slot1), pl, ws_[k]) : HG1X::identity();
     };
     auto f_b2 = std::async(std::launch::async, [&] {
-      return plan_z_.sh.n ? host_finish<HG2X>((const HG2X*)(hw.data() + 4 * slot1), plan_z_) : HG2X::identity();
+      return plan_z_.sh.n ? host_finish<HG2X>((const HG2X*)(hw.data() + 4 * slot1), plan_z_, ws_[4]) : HG2X::identity();
     });
     auto f_h = std::async(std::launch::async, [&] { return hor1(0, plan_h_); });
     auto f_l = std::async(std::launch::async, [&] { return hor1(1, plan_z_); });
@@ -1132,7 +1132,7 @@ class Engine : public EngineBase {
     d2h(st_, hw.data(), d_win_.p, hw.size());
     stream_sync(st_);
     tm.collect(timings);
-    HX res = n ? host_finish<HX>((const HX*)hw.data(), plan_misc_) : HX::identity();
+    HX res = n ? host_finish<HX>((const HX*)hw.data(), plan_misc_, ws_[5]) : HX::identity();
     HA a = HX::to_affine(res);
     const size_t words = sizeof(A) / 4;
     uint32_t* o = (uint32_t*)out;
