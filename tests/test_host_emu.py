@@ -166,3 +166,20 @@ def test_reference_edge_programs(case, emu_lib):
     (the program shapes of the reference's own backend tests)."""
     from tests.util import check_backend_roundtrip, reference_edge_programs
     check_backend_roundtrip(emu_lib, *reference_edge_programs()[case])
+
+
+@pytest.mark.parametrize("dist", ["uniform", "bits"])
+def test_prove_synthetic_vs_c_oracle(dist, emu_lib, oracle_c):
+    """300-constraint synthetic circuit (both witness distributions: full-width and 90 % bits, the latter taking the
+    sparse 16-window path) against the ark-equivalent C prover; setup bytes equal the C oracle's key."""
+    from zokrates_b200 import synthetic
+    ctx = Context(0, 0, emu_lib)
+    r1, z = synthetic.make("bn128", 300, distribution=dist)
+    h = ctx.r1cs_load(r1.num_constraints, r1.num_instance, r1.num_witness, r1.matrices())
+    td = [3, 5, 7, 11, 13, 17, 19]
+    pk = ctx.setup(h, td)
+    assert pk == oracle_c.setup(0, r1, td)
+    ref, _ = oracle_c.prove(0, pk, r1, z, 111, 222, 32)
+    assert ctx.prove(ctx.pk_load(pk), h, z, 111, 222) == ref
+    parts = [ctx.prove_partial(ctx.pk_load(pk, k, 2), h, z) for k in range(2)]
+    assert ctx.finalize(ctx.pk_load(pk), np.concatenate(parts), 2, 111, 222) == ref
