@@ -246,3 +246,35 @@ def test_error_paths(cc):
 def test_reference_edge_programs(case, gpu_lib):
     from tests.util import check_backend_roundtrip, reference_edge_programs
     check_backend_roundtrip(None, *reference_edge_programs()[case])
+
+
+def test_file_level_generate_proof_tool(tmp_path, gpu_lib):
+    """`zkb-generate-proof -i out -w witness -p proving.key -j proof.json -e entropy` (the file-level drop-in for
+    zokrates_cli/src/ops/generate_proof.rs:95-202): program file, binary witness and ark-format key in, TaggedProof JSON
+    out — equal to the python oracle's proof for the same entropy (factorize.zok of BASELINE config 1)."""
+    import json
+    from tools import zkb_generate_proof as tool
+    from zokrates_b200 import ir, zir
+    c = BN254
+    a_, b_ = ir.Variable.new(0), ir.Variable.new(1)
+    prog = ir.Prog([ir.Parameter.private_(a_), ir.Parameter.public(b_)], 0, [ir.constraint(a_, a_, b_)], "bn128")
+    witness = ir.Interpreter().execute(prog, [337, 113569])
+    td = [11, 22, 33, 44, 55555, 3, 7]
+    kp = backend.B200.setup(prog, td)
+    (tmp_path / "out").write_bytes(zir.write_prog(prog))
+    (tmp_path / "witness").write_bytes(witness.write())
+    (tmp_path / "proving.key").write_bytes(kp.pk)
+    rc = tool.main(["-i", str(tmp_path / "out"), "-w", str(tmp_path / "witness"), "-p", str(tmp_path / "proving.key"),
+                    "-j", str(tmp_path / "proof.json"), "-e", "file-level"])
+    assert rc == 0
+    text = (tmp_path / "proof.json").read_text()
+    oprog = oir.Prog([(a_.id, True), (b_.id, False)], 0, [oir.Constraint([(a_.id, 1)], [(a_.id, 1)], [(b_.id, 1)])])
+    ow = oir.execute(c, oprog, [337, 113569])
+    r1cs_o, z = ark.synthesize(oprog, ow)
+    orng = ark.rng_from_entropy("file-level")
+    r, s = ark.fr_rand(c, orng), ark.fr_rand(c, orng)
+    exp = ark.trapdoor_expected_proof(c, r1cs_o, ark.Trapdoor(*td), z, r, s)
+    assert text == ark.tagged_proof_json(c, exp, [113569])
+    assert json.loads(text)["scheme"] == "g16" and json.loads(text)["curve"] == "bn128"
+    with pytest.raises(SystemExit, match="Could not open"):
+        tool.main(["-i", str(tmp_path / "missing")])
