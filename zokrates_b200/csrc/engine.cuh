@@ -30,7 +30,7 @@ struct k_fr_convert; struct k_spmv; struct k_ntt_dif; struct k_ntt_dit; struct k
 struct k_ntt_table; struct k_qap_pointwise; struct k_msm_digits; struct k_msm_scatter; struct k_msm_accum1;
 struct k_msm_accum2; struct k_msm_tree; struct k_msm_horner; struct k_pk_convert; struct k_final_a; struct k_final_b;
 struct k_final_c; struct k_final_d; struct k_point_out; struct k_field_op; struct k_setup_scalars; struct k_fixed_base;
-struct k_to_affine; struct k_copy; struct k_msm_table; struct k_msm_tree_coop;
+struct k_to_affine; struct k_copy; struct k_msm_table; struct k_msm_tree_coop; struct k_ntt_dif_tile; struct k_ntt_dit_tile;
 
 // ---------------------------------------------------------------------------------------------
 // stage timer: CUDA events on the engine stream (no-op in the host emulation)
@@ -311,8 +311,35 @@ class Engine : public EngineBase {
     return r;
   }
 
+  // Transforms of 2^10 and more points run as shared-memory tile passes (ntt_block_body: 10 stages per HBM round
+  // trip); smaller ones as register passes (3 stages per round trip).  ZKB_NTT_TILE_MIN / ZKB_NTT_MAXS: test knobs.
+  static uint32_t ntt_tile_min() {
+    const char* e = getenv("ZKB_NTT_TILE_MIN");   // read per call: the tests flip it inside one process
+    const uint32_t v = e ? (uint32_t)atoi(e) : NTT_TILE_LOG;
+    return v < NTT_TILE_LOG ? NTT_TILE_LOG : v;
+  }
+  static uint32_t ntt_max_s() {
+    const char* e = getenv("ZKB_NTT_MAXS");
+    const uint32_t v = e ? (uint32_t)atoi(e) : NTT_TILE_LOG;
+    return v < 5 ? 5 : v;
+  }
+  static bool ntt_tiled(uint32_t log_n) { return log_n >= ntt_tile_min(); }
+
   // natural -> bit-reversed
   void ntt_dif(Fr* x, const Fr* tw, uint32_t log_n) {
+    NttPass ps[8];
+    const uint32_t np = ntt_tiled(log_n) ? ntt_plan_passes(log_n, ntt_max_s(), ps) : 0;
+    if (np) {
+      const size_t tiles = ((size_t)1 << log_n) >> NTT_TILE_LOG;
+      const Fr* nul = nullptr;
+      for (uint32_t i = 0; i < np; i++) {   // top stage bits first
+        NttPass p = ps[i];
+        launch_block<k_ntt_dif_tile, NTT_BLOCK, NTT_TILE * sizeof(Fr)>(st_, tiles, p.nk + 2, ZKB_LAMBDA(uint32_t b, uint32_t t, uint32_t ph, void* sm) {
+          ntt_block_body<Fr, false>(x, tw, nul, p, (Fr*)sm, b, t, ph);
+        });
+      }
+      return;
+    }
     uint32_t h = (1u << log_n) >> 1, rem = log_n;
     const size_t n = (size_t)1 << log_n;
     while (rem > 0) {
@@ -325,8 +352,22 @@ class Engine : public EngineBase {
       rem -= K;
     }
   }
-  // bit-reversed -> natural
-  void ntt_dit(Fr* x, const Fr* tw, uint32_t log_n) {
+  // bit-reversed -> natural; `scale` (optional): x[i] *= scale[bitrev(i)] first (the coset shift between ifft and coset fft)
+  void ntt_dit(Fr* x, const Fr* tw, uint32_t log_n, const Fr* scale = nullptr) {
+    NttPass ps[8];
+    const uint32_t np = ntt_tiled(log_n) ? ntt_plan_passes(log_n, ntt_max_s(), ps) : 0;
+    if (np) {
+      const size_t tiles = ((size_t)1 << log_n) >> NTT_TILE_LOG;
+      for (uint32_t i = np; i-- > 0;) {     // low stage bits first
+        NttPass p = ps[i];
+        const Fr* sc = (i == np - 1) ? scale : nullptr;
+        launch_block<k_ntt_dit_tile, NTT_BLOCK, NTT_TILE * sizeof(Fr)>(st_, tiles, p.nk + 2, ZKB_LAMBDA(uint32_t b, uint32_t t, uint32_t ph, void* sm) {
+          ntt_block_body<Fr, true>(x, tw, sc, p, (Fr*)sm, b, t, ph);
+        });
+      }
+      return;
+    }
+    if (scale) launch<k_ntt_scale>(st_, (size_t)1 << log_n, ZKB_LAMBDA(size_t t) { ntt_scale_brev_body<Fr>(x, scale, log_n, (uint32_t)t); });
     uint32_t h = 1, rem = log_n;
     const size_t n = (size_t)1 << log_n;
     while (rem > 0) {
@@ -476,8 +517,7 @@ class Engine : public EngineBase {
     for (int k = 0; k < 3; k++) {
       Fr* x = vec[k];
       ntt_dif(x, d.tw_inv.p, lg);
-      launch<k_ntt_scale>(st_, n, ZKB_LAMBDA(size_t t) { ntt_scale_brev_body<Fr>(x, t1, lg, (uint32_t)t); });
-      ntt_dit(x, d.tw_fwd.p, lg);
+      ntt_dit(x, d.tw_fwd.p, lg, t1);   // coset shift (g^k / n at the bit-reversed position) fused into the first pass
     }
     Fr* pa = r.a.p; const Fr* pb = r.b.p; const Fr* pc = r.c.p;
     Fr zinv = d.zinv;
@@ -587,12 +627,9 @@ class Engine : public EngineBase {
     const uint32_t* so = pl.sorted.p + (size_t)view * pl.sh.n * pl.sh.W;
     uint32_t* k0 = ws.key[0].p; X* v0 = (X*)ws.val[0].p;
     if (tm && accum_name) tm->begin(accum_name);
-    // G2 (Fq2 coordinates) wants > 200 registers: cap it so that 3 blocks (12 warps) stay resident per SM
+    // G2 (Fq2 coordinates) wants > 200 registers: two blocks per SM (3 and 4 were measured equal, profiles/r01_tuning_log.md)
     if (sizeof(F) > sizeof(Fq)) {
-      static const int minb = getenv("ZKB_G2_MINB") ? atoi(getenv("ZKB_G2_MINB")) : ZKB_G2_MINB;  // tuning knob
-      if (minb >= 4) launch<k_msm_accum1, 128, 4>(st_, nt1, ZKB_LAMBDA(size_t t) { msm_accum1_body<F>(NB, T1, of, so, pts, buckets, k0, v0, nt1, (uint32_t)t); });
-      else if (minb == 3) launch<k_msm_accum1, 128, 3>(st_, nt1, ZKB_LAMBDA(size_t t) { msm_accum1_body<F>(NB, T1, of, so, pts, buckets, k0, v0, nt1, (uint32_t)t); });
-      else launch<k_msm_accum1, 128, 2>(st_, nt1, ZKB_LAMBDA(size_t t) { msm_accum1_body<F>(NB, T1, of, so, pts, buckets, k0, v0, nt1, (uint32_t)t); });
+      launch<k_msm_accum1, 128, ZKB_G2_MINB>(st_, nt1, ZKB_LAMBDA(size_t t) { msm_accum1_body<F>(NB, T1, of, so, pts, buckets, k0, v0, nt1, (uint32_t)t); });
     } else {
       launch<k_msm_accum1>(st_, nt1, ZKB_LAMBDA(size_t t) { msm_accum1_body<F>(NB, T1, of, so, pts, buckets, k0, v0, nt1, (uint32_t)t); });
     }

@@ -94,6 +94,137 @@ ZKB_HDN inline void ntt_dit_body(Fr* x, const Fr* tw, uint32_t log_n, uint32_t h
   for (uint32_t m = 0; m < R; m++) x[i0 + (size_t)m * h0] = e[m];
 }
 
+
+// ---- shared-memory pass: S consecutive radix-2 stages on 1024-element tiles --------------------------------
+// The register passes above move the whole vector through HBM once per 3 stages (7 round trips for n = 2^20).
+// Here a block keeps a tile of 1024 elements (32 KB) in shared memory and runs S <= 10 stages on it, so a
+// transform is ceil(log n / 10) round trips.  The stages of a pass act on index bits [lo_bit, lo_bit + S); a tile
+// is G = 1024 >> S independent groups of 2^S elements.  For lo_bit > 0 the G groups are neighbours in the low
+// index bits (runs of G contiguous elements in HBM, local position j * G + g); for lo_bit == 0 a tile is 1024
+// contiguous elements (local position g * 2^S + j).  Phase 0 loads (optionally scaling by table[bitrev(i)], the
+// coset shift between ifft and coset fft), phases 1..nk run K[p] <= 3 stages on 8 register-resident elements per
+// step exactly like ntt_dif_body / ntt_dit_body, the last phase stores.  In place: tiles are disjoint.
+struct NttPass {
+  uint32_t log_n, lo_bit, S, nk;
+  uint32_t K[4];
+};
+static constexpr uint32_t NTT_TILE_LOG = 10, NTT_TILE = 1u << NTT_TILE_LOG, NTT_BLOCK = 128;
+
+ZKB_HD uint32_t ntt_tile_global(const NttPass& ps, uint32_t block, uint32_t e, uint32_t* j_out, uint32_t* low_out) {
+  const uint32_t G = NTT_TILE >> ps.S;
+  if (ps.lo_bit == 0) {
+    *j_out = e & ((1u << ps.S) - 1u);
+    *low_out = 0;
+    return (block << NTT_TILE_LOG) | e;
+  }
+  const uint32_t per_hi = (1u << ps.lo_bit) / G;  // tiles per value of the high index bits
+  const uint32_t hi = block / per_hi, lb = block % per_hi;
+  const uint32_t j = e / G, g = e % G;
+  *j_out = j;
+  *low_out = lb * G + g;
+  return (hi << (ps.lo_bit + ps.S)) | (j << ps.lo_bit) | (lb * G + g);
+}
+
+// one compute phase: K stages (compile-time, so the 2^K elements stay in registers) starting after `done` local stages
+template <class Fr, bool DIT, int K>
+ZKB_HDN inline void ntt_block_stages(const Fr* tw, const NttPass& ps, Fr* sm, uint32_t block, uint32_t thread, uint32_t done) {
+  constexpr uint32_t R = 1u << K;
+  const uint32_t G = NTT_TILE >> ps.S;
+  const uint32_t lg_hmin = DIT ? done : ps.S - done - K;   // smallest local half-span of this phase
+  const uint32_t hmin = 1u << lg_hmin;
+  const uint32_t per_group = (1u << ps.S) >> K;             // work items per group
+  uint32_t low_base = 0;
+  if (ps.lo_bit) low_base = (block % ((1u << ps.lo_bit) / G)) * G;
+  for (uint32_t tt = thread; tt < (NTT_TILE >> K); tt += NTT_BLOCK) {
+    uint32_t g, jj;
+    if (ps.lo_bit) { g = tt % G; jj = tt / G; } else { jj = tt % per_group; g = tt / per_group; }
+    const uint32_t off = jj & (hmin - 1), blk = jj >> lg_hmin;
+    const uint32_t j0 = (blk << (lg_hmin + K)) | off;
+    const uint32_t low = ps.lo_bit ? low_base + g : 0;
+    Fr e[R];
+#pragma unroll
+    for (uint32_t m = 0; m < R; m++) {
+      const uint32_t j = j0 + m * hmin;
+      e[m] = sm[ps.lo_bit ? j * G + g : (g << ps.S) + j];
+    }
+#pragma unroll
+    for (int q = 0; q < K; q++) {
+      const uint32_t hm = DIT ? (1u << q) : (1u << (K - 1 - q));
+      const uint32_t lg_h = lg_hmin + (DIT ? q : K - 1 - q) + ps.lo_bit;   // log2 of the global half-span
+      const uint32_t sh = ps.log_n - 1 - lg_h;                              // exponent step n / 2h
+#pragma unroll
+      for (uint32_t m = 0; m < R; m++) {
+        if (m & hm) continue;
+        const uint32_t imod = ((off + (m & (hm - 1)) * hmin) << ps.lo_bit) | low;
+        const uint32_t ex = imod << sh;
+        Fr u = e[m];
+        if (DIT) {
+          Fr v = ex ? Fr::mul(e[m + hm], tw[ex]) : e[m + hm];
+          e[m] = Fr::add(u, v);
+          e[m + hm] = Fr::sub(u, v);
+        } else {
+          Fr v = e[m + hm];
+          e[m] = Fr::add(u, v);
+          Fr d = Fr::sub(u, v);
+          e[m + hm] = ex ? Fr::mul(d, tw[ex]) : d;
+        }
+      }
+    }
+#pragma unroll
+    for (uint32_t m = 0; m < R; m++) {
+      const uint32_t j = j0 + m * hmin;
+      sm[ps.lo_bit ? j * G + g : (g << ps.S) + j] = e[m];
+    }
+  }
+}
+
+template <class Fr, bool DIT>
+ZKB_HDN inline void ntt_block_body(Fr* x, const Fr* tw, const Fr* scale, NttPass ps, Fr* sm, uint32_t block, uint32_t thread,
+                                   uint32_t phase) {
+  if (phase == 0 || phase == ps.nk + 1) {
+    for (uint32_t k = 0; k < NTT_TILE / NTT_BLOCK; k++) {
+      const uint32_t e = thread + k * NTT_BLOCK;
+      uint32_t j, low;
+      const uint32_t gi = ntt_tile_global(ps, block, e, &j, &low);
+      if (phase == 0) {
+        Fr v = x[gi];
+        if (scale) v = Fr::mul(v, scale[bitrev32(gi, ps.log_n)]);
+        sm[e] = v;
+      } else {
+        x[gi] = sm[e];
+      }
+    }
+    return;
+  }
+  uint32_t done = 0;
+  for (uint32_t p = 1; p < phase; p++) done += ps.K[p - 1];
+  switch (ps.K[phase - 1]) {
+    case 3: ntt_block_stages<Fr, DIT, 3>(tw, ps, sm, block, thread, done); break;
+    case 2: ntt_block_stages<Fr, DIT, 2>(tw, ps, sm, block, thread, done); break;
+    default: ntt_block_stages<Fr, DIT, 1>(tw, ps, sm, block, thread, done); break;
+  }
+}
+
+// split log_n stage bits into passes of at most max_s bits (balanced), top pass first; returns the pass count
+// (0: this split cannot be tiled — the caller uses the register passes)
+inline uint32_t ntt_plan_passes(uint32_t log_n, uint32_t max_s, NttPass out[8]) {
+  if (max_s > NTT_TILE_LOG) max_s = NTT_TILE_LOG;
+  const uint32_t np = (log_n + max_s - 1) / max_s;
+  uint32_t hi = log_n;
+  for (uint32_t i = 0; i < np; i++) {
+    uint32_t S = log_n / np + (i < log_n % np ? 1 : 0);
+    NttPass& p = out[i];
+    p.log_n = log_n; p.S = S; p.lo_bit = hi - S;
+    p.nk = (S + 2) / 3;
+    for (uint32_t k = 0; k < 4; k++) p.K[k] = 0;
+    for (uint32_t k = 0; k < p.nk; k++) p.K[k] = S / p.nk + (k < S % p.nk ? 1 : 0);
+    hi -= S;
+    // interleaved groups need runs of G = 1024 >> S elements inside the low index bits
+    if (p.lo_bit && p.lo_bit + S < NTT_TILE_LOG) return 0;
+  }
+  return np;
+}
+
 // x[i] *= table[bitrev(i)]  (coset shift / 1/n scaling applied to a bit-reversed coefficient vector)
 template <class Fr>
 ZKB_HDN inline void ntt_scale_brev_body(Fr* x, const Fr* table, uint32_t log_n, uint32_t t) {

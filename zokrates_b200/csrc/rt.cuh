@@ -82,6 +82,26 @@ inline void launch_phased(Stream st, size_t nblocks, uint32_t nphases, Fn fn) {
   ZKB_CUDA(cudaGetLastError());
 }
 
+// Block kernels with static shared memory: `nphases` steps separated by __syncthreads(); fn(block, thread, phase, smem).
+// Registers do not live across phases (the body is re-entered per phase); the host emulation gives every block a
+// heap buffer and runs phase by phase.
+template <class Tag, int BLOCK, int SMEM_BYTES, class Fn>
+__global__ void __launch_bounds__(BLOCK) zkb_block_kernel(uint32_t nphases, Fn fn) {
+  __shared__ __align__(16) uint8_t smem[SMEM_BYTES];
+  for (uint32_t ph = 0; ph < nphases; ph++) {
+    fn((uint32_t)blockIdx.x, (uint32_t)threadIdx.x, ph, (void*)smem);
+    __syncthreads();
+  }
+}
+template <class Tag, int BLOCK, int SMEM_BYTES, class Fn>
+inline void launch_block(Stream st, size_t nblocks, uint32_t nphases, Fn fn) {
+  if (nblocks == 0) return;
+  launch_counter()++;
+  if (nblocks > 0x7fffffffull) throw Error(ZKB_E_ARG, "grid too large");
+  zkb_block_kernel<Tag, BLOCK, SMEM_BYTES, Fn><<<(unsigned)nblocks, BLOCK, 0, st.s>>>(nphases, fn);
+  ZKB_CUDA(cudaGetLastError());
+}
+
 inline void* dev_alloc(size_t bytes) {
   void* p = nullptr;
   if (bytes == 0) bytes = 16;
@@ -151,6 +171,16 @@ inline void launch_phased(Stream, size_t nblocks, uint32_t nphases, Fn fn) {
   for (size_t b = 0; b < nblocks; b++)
     for (uint32_t ph = 0; ph < nphases; ph++)
       for (uint32_t t = 0; t < (uint32_t)BLOCK; t++) fn((uint32_t)b, t, ph);
+}
+template <class Tag, int BLOCK, int SMEM_BYTES, class Fn>
+inline void launch_block(Stream, size_t nblocks, uint32_t nphases, Fn fn) {
+  if (nblocks) launch_counter()++;
+  void* smem = malloc(SMEM_BYTES);
+  if (!smem) throw Error(ZKB_E_OOM, "malloc");
+  for (size_t b = 0; b < nblocks; b++)
+    for (uint32_t ph = 0; ph < nphases; ph++)
+      for (uint32_t t = 0; t < (uint32_t)BLOCK; t++) fn((uint32_t)b, t, ph, smem);
+  free(smem);
 }
 inline void* dev_alloc(size_t bytes) {
   void* p = malloc(bytes ? bytes : 16);
