@@ -45,43 +45,58 @@ def env_int(name, default):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md).  Started before the warm-up (nvidia-smi takes a few
+    hundred ms to come up, longer than a short timed region); every sample carries the host time it was read at and
+    only those inside the marked timed windows are reported (all load samples if a window caught none)."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index=0):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index=0, period_ms=50):
+        self.index, self.period_ms, self.proc, self.lines, self.windows = index, period_ms, None, [], []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", str(self.period_ms), "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line)
+            self.lines.append((time.perf_counter(), line))
+
+    def mark(self, t0, t1):
+        self.windows.append((t0, t1))
 
     def stop(self):
         if self.proc:
+            time.sleep(2.5 * self.period_ms / 1e3)
             self.proc.terminate()
-        sm, mx, reasons = [], 0, set()
-        for line in self.lines:
+        rows = []
+        for ts, line in self.lines:
             p = [x.strip() for x in line.split(",")]
             if len(p) < 9:
                 continue
             try:
-                sm.append(float(p[1])); mx = max(mx, float(p[2]))
+                rows.append((ts, float(p[1]), float(p[2]), float(p[3]), p[5:9]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+        inside = [r for r in rows if any(a <= r[0] <= b + self.period_ms / 1e3 for a, b in self.windows)]
+        scope = "timed region"
+        if not inside:                       # fall back to the samples taken under load (warm-up + timed steps)
+            inside = [r for r in rows if r[3] > 250.0] or rows
+            scope = "warm-up + timed steps (no sample fell inside the timed windows)"
+        reasons = set()
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        sm = [r[1] for r in inside]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max((r[2] for r in inside), default=None),
+                "reasons": sorted(reasons), "samples": len(sm), "scope": scope,
+                "power_w_max": max((r[3] for r in inside), default=None)}
 
 
 def load_oracle():
@@ -238,15 +253,19 @@ def main():
             elapsed = float(tt.item())
         return elapsed, {k: v / steps for k, v in stage.items()}, ctx.launch_count() - launches0, proof
 
-    for _ in range(args.warmup):
-        step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step_resident()
+    tw0 = time.perf_counter()
     t_res, stage_res, launches, proof = timed(step_resident, args.steps)
+    sampler.mark(tw0, time.perf_counter())
     for _ in range(2):
         step_e2e()
+    tw0 = time.perf_counter()
     t_e2e, stage_e2e, _, proof2 = timed(step_e2e, args.steps)
+    sampler.mark(tw0, time.perf_counter())
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0 and proof != proof2:
         raise SystemExit("resident and e2e proofs differ")

@@ -28,9 +28,9 @@ namespace zkb {
 // kernel name tags (show up in ncu / nsys kernel names)
 struct k_fr_convert; struct k_spmv; struct k_ntt_dif; struct k_ntt_dit; struct k_ntt_scale; struct k_ntt_brev;
 struct k_ntt_table; struct k_qap_pointwise; struct k_msm_digits; struct k_msm_scatter; struct k_msm_accum1;
-struct k_msm_accum2; struct k_msm_tree; struct k_msm_horner; struct k_pk_convert; struct k_final_a; struct k_final_b;
+struct k_msm_accum2; struct k_msm_bitsum; struct k_pk_convert; struct k_final_a; struct k_final_b;
 struct k_final_c; struct k_final_d; struct k_point_out; struct k_field_op; struct k_setup_scalars; struct k_fixed_base;
-struct k_to_affine; struct k_copy; struct k_msm_table; struct k_msm_tree_coop; struct k_ntt_dif_tile; struct k_ntt_dit_tile;
+struct k_to_affine; struct k_copy; struct k_msm_table; struct k_ntt_dif_tile; struct k_ntt_dit_tile;
 
 // ---------------------------------------------------------------------------------------------
 // stage timer: CUDA events on the engine stream (no-op in the host emulation)
@@ -582,13 +582,14 @@ class Engine : public EngineBase {
 
   // per-MSM scratch so that the latency-bound tails of different MSMs can overlap
   struct MsmWs {
-    DevBuf<uint8_t> buckets, val[2], tree[4], coop[4];
+    DevBuf<uint8_t> buckets, val[2], tree[4];
     DevBuf<uint32_t> key[2];
     Stream tail;          // high-priority side stream for accum2 / tree
     Event acc_done, tail_done;
     bool has_stream = false;
-    // filled by msm_tail: the GPU tree stopped at `tree_cnt` nodes per window (each spanning 2^tree_bits buckets)
-    uint32_t tree_cnt = 1, tree_bits = 0;
+    // filled by msm_tail: the bit-sum reduction ran `tree_lvls` levels and left `tree_cnt` block totals per window
+    uint32_t tree_cnt = 1, tree_lvls = 0;
+    size_t out_entries = 0;   // XYZZ entries of the result slot the host has to read: (1 + 3 * tree_lvls) * W * tree_cnt
   };
   static constexpr int NUM_WS = 6;   // h, l, a, b1, b2, misc
   MsmWs ws_[NUM_WS];
@@ -637,11 +638,10 @@ class Engine : public EngineBase {
     ws.acc_done.record(st_);
   }
 
-  // phase 2 (side stream): reduce chunk-boundary partials, then the per-window bucket tree.  Latency-bound:
-  // a few thousand threads doing ~20 dependent point additions per level, so it runs on a high-priority
-  // stream underneath the next MSM's accumulation.
+  // phase 2 (side stream): reduce chunk-boundary partials, then the bucket reduction by bit sums.  Latency-bound
+  // (7 dependent point additions per level), so it runs on a high-priority stream underneath the next MSM's accumulation.
   template <class F>
-  void msm_tail(const MsmPlan& pl, MsmWs& ws, XYZZ<F>* win_out /* 2 W entries */, StageTimer* tm = nullptr, const char* tail_name = nullptr) {
+  void msm_tail(const MsmPlan& pl, MsmWs& ws, XYZZ<F>* win_out /* MAXW entries */, StageTimer* tm = nullptr, const char* tail_name = nullptr) {
     typedef XYZZ<F> X;
     if (pl.sh.n == 0) return;
     Stream ts = tail_stream(ws);
@@ -661,64 +661,30 @@ class Engine : public EngineBase {
       L = 2 * nt;
       cur ^= 1;
     }
-    const uint32_t lr = 3;
-    size_t first = (size_t)W * ((B + 7) / 8);
-    for (int k = 0; k < 4; k++) ws.tree[k].ensure(first * sizeof(X));
-    const X* inA = buckets; const X* inWt = nullptr;
-    uint32_t cnt = B, lvl = 0, bits_done = 0;
-    int pp = 0;
-    // cooperative upper levels shorten the dependent chain 3x but add work that competes with the accumulate kernels:
-    // measured neutral-to-negative on B200 (profiles/r01_tuning_log.md): compiled only with -DZKB_TREE_COOP_BUILD
-    static const int coop = getenv("ZKB_TREE_COOP") ? atoi(getenv("ZKB_TREE_COOP")) : 0;
-    // the last few hundred nodes are cheaper on a host core (0.5 us per addition instead of ~8 us of dependent latency)
-    // (a G2 addition costs 1.3 us on the host, so the G2 tree goes further down on the GPU — its tail is not the last to finish)
+    // bucket reduction by bit sums (msm.cuh::msm_bitsum_body): one launch per 3 index bits, 7 dependent additions each
+    const size_t first = (size_t)W * (B >> 3);
+    ws.tree[0].ensure((first + 1) * sizeof(X)); ws.tree[1].ensure((first / 8 + 1) * sizeof(X));
+    ws.tree[2].ensure((3 * first + 1) * sizeof(X)); ws.tree[3].ensure((3 * first + 1) * sizeof(X));
+    const X* inA = buckets; const X* inP = nullptr;
+    uint32_t cnt = B, lvl = 0;
+    // a G2 addition costs 1.3 us on a host core against 0.45 us in G1, and the G2 tail is never the last to finish:
+    // run it further down on the GPU
     const size_t host_nodes = sizeof(F) > sizeof(Fq) ? HOST_TREE_NODES / 8 : HOST_TREE_NODES;
-    while (cnt > 1 && (size_t)W * cnt > host_nodes) {
-      X* oA = (X*)ws.tree[pp].p; X* oW = (X*)ws.tree[pp + 1].p;
-      const X* iA = inA; const X* iW = inWt;
-      uint32_t ci = cnt;
-#if !defined(ZKB_TREE_COOP_BUILD)
-      (void)coop;
-      {
-#else
-      if (lvl == 0 || !coop) {
-#endif
-        // leaves: many nodes, sequential fan-in 8 per thread (throughput-bound)
-        uint32_t cnt_out = (cnt + 7) / 8;
-        uint32_t lv = lvl;
-        launch<k_msm_tree>(ts, (size_t)W * cnt_out, ZKB_LAMBDA(size_t t) { msm_tree_body<F>(W, ci, lr, lv, iA, iW, oA, oW, (uint32_t)t); });
-        cnt = cnt_out; bits_done += lr;
-      }
-#if defined(ZKB_TREE_COOP_BUILD)
-      else {
-        // upper levels: few nodes, 16 threads per node with log-step scan / reduction (latency-bound)
-        const uint32_t f = 4, Fn = 16;
-        uint32_t cnt_out = (cnt + Fn - 1) / Fn;
-        size_t slots = (size_t)W * cnt_out * Fn;
-        constexpr int CB = 128;
-        size_t nblocks = (slots + CB - 1) / CB;
-        for (int k = 0; k < 4; k++) ws.coop[k].ensure(nblocks * CB * sizeof(X));
-        X* s0 = (X*)ws.coop[0].p; X* s1 = (X*)ws.coop[1].p; X* vv = (X*)ws.coop[2].p; X* rr = (X*)ws.coop[3].p;
-        uint32_t shift = bits_done;
-        launch_phased<k_msm_tree_coop, CB>(ts, nblocks, 2 * f + 2, ZKB_LAMBDA(uint32_t b, uint32_t t, uint32_t ph) {
-          msm_tree_coop_body<F>(W, ci, f, shift, iA, iW, oA, oW, s0, s1, vv, rr, CB, b, t, ph);
-        });
-        cnt = cnt_out; bits_done += f;
-      }
-#endif
-      inA = oA; inWt = oW; lvl++;
-      pp ^= 2;
+    while (cnt >= 8 && (size_t)W * cnt > host_nodes) {
+      X* oA = (X*)ws.tree[lvl & 1].p; X* oP = (X*)ws.tree[2 + (lvl & 1)].p;
+      const X* iA = inA; const X* iP = inP;
+      const uint32_t ci = cnt, np = 3 * lvl;
+      const size_t threads = (size_t)(4 + np) * W * (cnt >> 3);
+      launch<k_msm_bitsum>(ts, threads, ZKB_LAMBDA(size_t t) { msm_bitsum_body<F>(W, ci, np, iA, iP, oA, oP, (uint32_t)t); });
+      inA = oA; inP = oP; cnt >>= 3; lvl++;
     }
-    // remaining nodes (A, Wt) -> caller's slot; the host finishes the tree and the 2^(c w) Horner (fp64.cuh)
-    ws.tree_cnt = cnt; ws.tree_bits = bits_done;
+    // result slot: [A : W*cnt][pending 0 : W*cnt] ... [pending 3*lvl-1 : W*cnt]; the host finishes (host_finish)
+    ws.tree_cnt = cnt; ws.tree_lvls = lvl;
     const size_t nodes = (size_t)W * cnt;
-    if (lvl == 0) {  // tiny bucket set: nothing ran on the GPU, the nodes are the buckets themselves (Wt = 0)
-      d2d(ts, win_out, buckets, nodes * sizeof(X));
-      dev_zero(ts, win_out + nodes, nodes * sizeof(X));
-    } else {
-      d2d(ts, win_out, inA, nodes * sizeof(X));
-      d2d(ts, win_out + nodes, inWt, nodes * sizeof(X));
-    }
+    ws.out_entries = nodes * (1 + 3 * (size_t)lvl);
+    if (ws.out_entries > MAXW) throw Error(ZKB_E_INTERNAL, "msm result slot overflow");
+    d2d(ts, win_out, inA, nodes * sizeof(X));
+    if (lvl) d2d(ts, win_out + nodes, inP, nodes * 3 * lvl * sizeof(X));
     if (tm && tail_name) tm->end_on(ts, span);
     ws.tail_done.record(ts);
   }
@@ -730,58 +696,30 @@ class Engine : public EngineBase {
     msm_tail<F>(pl, ws, win_out, tm, tail_name);
   }
 
-  // Host finish of one MSM: per window, sum_k [Wt_k + 2^bits * k * A_k] + sum_k A_k over the `cnt` remaining tree
-  // nodes (running sums), then result = sum_w 2^(c w) S_w.
-  static constexpr size_t HOST_TREE_NODES = 256;
+  // Host finish of one MSM.  Per window: total = sum_k A_k, hi = sum_k k A_k (running sums), S_bit = sum_k P_bit[k];
+  //   sum_j (j + 1) B_j = total + sum_bit 2^bit S_bit + 2^(3 L) hi    (Horner from the top bit),
+  // then result = sum_w 2^(c w) (window sum).  A few hundred point additions on a host core.
+  static constexpr size_t HOST_TREE_NODES = 32;
   template <class HX>
-  static HX host_finish(const HX* nodes, const MsmPlan& pl, const MsmWs& ws) {
-    const uint32_t W = pl.sh.pre ? 1 : pl.sh.W, cnt = ws.tree_cnt, bits = ws.tree_bits, c = pl.sh.c;
-    const HX* A = nodes;
-    const HX* Wt = nodes + (size_t)W * cnt;
+  static HX host_finish(const HX* slot, const MsmPlan& pl, const MsmWs& ws) {
+    const uint32_t W = pl.sh.pre ? 1 : pl.sh.W, cnt = ws.tree_cnt, L = ws.tree_lvls, c = pl.sh.c;
+    const size_t nodes = (size_t)W * cnt;
+    const HX* A = slot;
     HX acc = HX::identity();
     for (uint32_t w = W; w-- > 0;) {
       for (uint32_t d = 0; d < c; d++) acc = HX::dbl(acc);
-      HX run = HX::identity(), wrel = HX::identity(), wsum = HX::identity();
-      const uint32_t SEG = 4;
-      if (cnt >= 64 && cnt % SEG == 0 && ((cnt / SEG) & (cnt / SEG - 1)) == 0) {
-        // four host threads, one quarter of the nodes each; quarter q has base q * cnt/4:
-        // sum k A_k = sum_q [ local + (q * cnt/4) * run_q ]
-        const uint32_t len = cnt / SEG;
-        HX r_[SEG], w_[SEG], s_[SEG];
-        auto part = [&](uint32_t q) {
-          HX rr = HX::identity(), ww = HX::identity(), ss = HX::identity();
-          for (uint32_t k = len; k-- > 0;) {
-            size_t idx = (size_t)w * cnt + q * len + k;
-            rr = HX::add(rr, A[idx]);
-            if (k > 0) ww = HX::add(ww, rr);
-            ss = HX::add(ss, Wt[idx]);
-          }
-          r_[q] = rr; w_[q] = ww; s_[q] = ss;
-        };
-        std::future<void> fut[SEG - 1];
-        for (uint32_t q = 1; q < SEG; q++) fut[q - 1] = std::async(std::launch::async, part, q);
-        part(0);
-        for (uint32_t q = 1; q < SEG; q++) fut[q - 1].get();
-        HX qsum = HX::identity(), qrun = HX::identity();       // sum_q q * run_q by running sums
-        for (uint32_t q = SEG; q-- > 0;) {
-          qrun = HX::add(qrun, r_[q]);
-          if (q > 0) qsum = HX::add(qsum, qrun);
-          wrel = HX::add(wrel, w_[q]);
-          wsum = HX::add(wsum, s_[q]);
-        }
-        run = qrun;
-        for (uint32_t t = len; t > 1; t >>= 1) qsum = HX::dbl(qsum);   // times len (a power of two: cnt is)
-        wrel = HX::add(wrel, qsum);
-      } else {
-        for (uint32_t k = cnt; k-- > 0;) {
-          run = HX::add(run, A[(size_t)w * cnt + k]);
-          if (k > 0) wrel = HX::add(wrel, run);
-          wsum = HX::add(wsum, Wt[(size_t)w * cnt + k]);
-        }
+      HX run = HX::identity(), hi = HX::identity();
+      for (uint32_t k = cnt; k-- > 0;) {
+        run = HX::add(run, A[(size_t)w * cnt + k]);
+        if (k > 0) hi = HX::add(hi, run);
       }
-      for (uint32_t d = 0; d < bits; d++) wrel = HX::dbl(wrel);
-      // bucket j holds weight j + 1: sum (j + 1) B_j = Wt + (relative weights) + A
-      acc = HX::add(acc, HX::add(HX::add(wsum, wrel), run));
+      for (uint32_t bit = 3 * L; bit-- > 0;) {
+        const HX* P = slot + nodes * (1 + (size_t)bit) + (size_t)w * cnt;
+        HX sb = HX::identity();
+        for (uint32_t k = 0; k < cnt; k++) sb = HX::add(sb, P[k]);
+        hi = HX::add(HX::dbl(hi), sb);
+      }
+      acc = HX::add(acc, HX::add(hi, run));   // bucket j holds weight j + 1
     }
     return acc;
   }
@@ -963,7 +901,7 @@ class Engine : public EngineBase {
   MsmPlan plan_z_, plan_h_;
   DevBuf<Fr> scratch_a_, scratch_b_;
   DevBuf<uint8_t> d_win_;
-  static constexpr uint32_t MAXW = 256;  // result slot: 2 x (at most HOST_TREE_NODES tree nodes per MSM)
+  static constexpr uint32_t MAXW = 1024;  // result slot entries per MSM: (1 + 3 levels) * W * tree_cnt <= 19 * 32
 
   struct HostPartial {  // same layout as Partial
     HG1X h, l, a, b1;
@@ -996,7 +934,7 @@ class Engine : public EngineBase {
     } else if (!r.has_z) {
       throw Error(ZKB_E_ARG, "no resident assignment");
     }
-    const size_t slot1 = 2 * MAXW * sizeof(G1X), slot2 = 2 * MAXW * sizeof(G2X);
+    const size_t slot1 = MAXW * sizeof(G1X), slot2 = MAXW * sizeof(G2X);
     d_win_.ensure(4 * slot1 + slot2);
     G1X* w_h = (G1X*)d_win_.p;
     G1X* w_l = (G1X*)(d_win_.p + slot1);
@@ -1011,9 +949,14 @@ class Engine : public EngineBase {
       wm_stream_ = (e && atoi(e) == 0) ? stream_create() : stream_create_high_priority();
       has_wm_stream_ = true;
     }
-    ev_z_ready_.record(st_);
+    // With one or two ranks the witness map has several milliseconds of slack (h is needed after four accumulate
+    // kernels), while the digit/sort plan of z is on the critical path and bandwidth-bound like the witness map: let the
+    // plan run alone first.  With more ranks the witness map itself is the critical path and starts at once.
+    static const int wm_early_env = getenv("ZKB_WM_EARLY") ? atoi(getenv("ZKB_WM_EARLY")) : -1;
+    const bool wm_early = wm_early_env >= 0 ? wm_early_env != 0 : pk.world > 2;
     StageTimer tm2(wm_stream_);
-    {
+    auto enqueue_witness_map = [&]() {
+      ev_z_ready_.record(st_);
       StreamScope sc(st_, wm_stream_);
       ev_z_ready_.wait(st_);
       witness_map_dev(r, tm2);
@@ -1021,10 +964,12 @@ class Engine : public EngineBase {
       plan_build(plan_h_, r.h.p + pk.hlo, pk.hhi - pk.hlo, 1, nullptr, pk.pre_ch);
       tm2.end();
       ev_h_ready_.record(st_);
-    }
+    };
+    if (wm_early) enqueue_witness_map();
     tm.begin("msm_plan_z");
     plan_build(plan_z_, r.z_canon.p + 1 + pk.lo, pk.hi - pk.lo, 3, pk.skip.p, r.sparse_z ? 0 : pk.pre_cz);
     tm.end();
+    if (!wm_early) enqueue_witness_map();
     msm_exec<Fq2>(plan_z_, pk.b2.p, w_b2, ws_[4], &tm, "accum1_g2_b2", 2, "tail_g2_b2");
     msm_exec<Fq>(plan_z_, pk.l.p, w_l, ws_[1], &tm, "accum1_g1_l", 0, "tail_g1_l");
     msm_exec<Fq>(plan_z_, pk.a.p, w_a, ws_[2], &tm, "accum1_g1_a", 1, "tail_g1_a");
@@ -1038,7 +983,13 @@ class Engine : public EngineBase {
     tm.end();
     std::vector<uint8_t> hw(4 * slot1 + slot2);
     tm.begin("d2h_windows");
-    d2h(st_, hw.data(), d_win_.p, hw.size());
+    {  // only the entries each tail produced (tree_cnt block totals + the pending bit-sum arrays)
+      const size_t offs[5] = {0, slot1, 2 * slot1, 3 * slot1, 4 * slot1};
+      const size_t esz[5] = {sizeof(G1X), sizeof(G1X), sizeof(G1X), sizeof(G1X), sizeof(G2X)};
+      const MsmPlan* pls[5] = {&plan_h_, &plan_z_, &plan_z_, &plan_z_, &plan_z_};
+      for (int k = 0; k < 5; k++)
+        if (pls[k]->sh.n) d2h(st_, hw.data() + offs[k], d_win_.p + offs[k], ws_[k].out_entries * esz[k]);
+    }
     tm.end();
     stream_sync(st_);
     tm.collect(timings);
@@ -1153,7 +1104,7 @@ class Engine : public EngineBase {
     StageTimer tm(st_);
     msm_pts_.ensure(n * sizeof(A) + 16);
     msm_scalars_.ensure(n + 1);
-    d_win_.ensure(2 * MAXW * sizeof(X));
+    d_win_.ensure(MAXW * sizeof(X));
     A* pts = (A*)msm_pts_.p;
     h2d(st_, pts, points, n * sizeof(A));
     h2d(st_, msm_scalars_.p, scalars, n * FRB);
@@ -1165,8 +1116,8 @@ class Engine : public EngineBase {
     msm_exec<F>(plan_misc_, pts, (X*)d_win_.p, ws_[5], &tm, "accum1");
     ws_[5].tail_done.wait(st_);
     tm.end();
-    std::vector<uint8_t> hw(2 * MAXW * sizeof(X));
-    d2h(st_, hw.data(), d_win_.p, hw.size());
+    std::vector<uint8_t> hw(MAXW * sizeof(X));
+    d2h(st_, hw.data(), d_win_.p, ws_[5].out_entries * sizeof(X));
     stream_sync(st_);
     tm.collect(timings);
     HX res = n ? host_finish<HX>((const HX*)hw.data(), plan_misc_, ws_[5]) : HX::identity();

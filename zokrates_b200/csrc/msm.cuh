@@ -261,97 +261,38 @@ ZKB_HDN inline void msm_table_body(const Affine<F>* pts, Affine<F>* table, uint3
   }
 }
 
-// ---- bucket tree: per window sum_j (j+1) * bucket[j] via (A, Wt) pairs --------------------------
-// Level `lvl` (0-based) combines groups of Lr = 2^lr children.  A child at level lvl covers
-// S = Lr^lvl original buckets.  A = plain sum, Wt = sum (index - base) * bucket.
+// ---- bucket reduction: per window sum_j (j+1) * bucket[j] by BIT SUMS ---------------------------------
+// sum_j j B_j = sum_bit 2^bit * S_bit with S_bit = sum of the buckets whose index has that bit set, so the weighted sum
+// needs no weighted arithmetic on the device at all — only plain sums over subsets, which reduce in parallel with a
+// dependent chain of 7 additions per level (the previous (sum, weighted-sum) tree ran 23 per level plus 3*lvl doublings).
+// One level groups 8 consecutive entries (3 index bits) and is ONE launch of uniform "masked 8-sums":
+//   role 0      : A'[k]      = sum of all 8 entries of A[8k..8k+8)            (block totals, feed the next level)
+//   role 1+b    : P_new_b[k] = sum of the entries i of that block with bit b of i set   (b = 0, 1, 2)
+//   role 4+r    : P_r'[k]    = sum of all 8 entries of the pending array P_r  (plain reduction of older bit sums)
+// so every array has the same length at every level.  After L levels the host holds A (cnt entries) and 3L pending
+// arrays per window and finishes with a few hundred additions:  S_(3l+b) = sum_k P_(3l+b)[k],
+//   sum_j (j+1) B_j = total + Horner_bits(S) + 2^(3L) * sum_k k A[k]   (engine.cuh::host_finish).
+// Pending array r of the input holds bit 3*(r/3) + r%3; the three new arrays are appended after the npend old ones.
 template <class F>
-ZKB_HDN inline void msm_tree_body(uint32_t W, uint32_t cnt_in, uint32_t lr, uint32_t lvl, const XYZZ<F>* inA,
-                                  const XYZZ<F>* inWt, XYZZ<F>* outA, XYZZ<F>* outWt, uint32_t t) {
-  const uint32_t Lr = 1u << lr;
-  const uint32_t cnt_out = (cnt_in + Lr - 1) >> lr;
-  if (t >= W * cnt_out) return;
-  uint32_t w = t / cnt_out, k = t % cnt_out;
-  const XYZZ<F>* A = inA + (size_t)w * cnt_in;
-  uint32_t lo = k << lr;
-  uint32_t hi = lo + Lr < cnt_in ? lo + Lr : cnt_in;
-  XYZZ<F> run = XYZZ<F>::identity(), wrel = XYZZ<F>::identity(), wsum = XYZZ<F>::identity();
-  for (uint32_t i = hi; i-- > lo;) {
-    run = XYZZ<F>::add(run, A[i]);
-    if (i > lo) wrel = XYZZ<F>::add(wrel, run);
-    if (lvl > 0) wsum = XYZZ<F>::add(wsum, inWt[(size_t)w * cnt_in + i]);
-  }
-  for (uint32_t d = 0; d < lr * lvl; d++) wrel = XYZZ<F>::dbl_ni(wrel);  // times S = 2^(lr*lvl)
-  outA[(size_t)w * cnt_out + k] = run;
-  outWt[(size_t)w * cnt_out + k] = XYZZ<F>::add(wsum, wrel);
-}
-
-// ---- cooperative tree level: F = 2^f children per node, F threads per node -----------------------
-// The sequential node above costs 3 F dependent additions; here the suffix sums are a log-step scan and
-// the two totals a log-step reduction: 3 f dependent additions per level (f bits of the bucket index).
-// Scratch (global, per thread slot): S0, S1 (scan ping-pong), V (weights), R (reduction).
-// Phases: 0 load | 1..f scan | f+1..2f reduce | 2f+1 finish.   Node n of window w <-> global node id w*cnt_out+n.
-template <class F>
-ZKB_HDN inline void msm_tree_coop_body(uint32_t W, uint32_t cnt_in, uint32_t f, uint32_t shift, const XYZZ<F>* inA,
-                                       const XYZZ<F>* inWt, XYZZ<F>* outA, XYZZ<F>* outWt, XYZZ<F>* S0, XYZZ<F>* S1, XYZZ<F>* V,
-                                       XYZZ<F>* R, uint32_t block_threads, uint32_t block, uint32_t thread, uint32_t phase) {
-  typedef XYZZ<F> X;
-  const uint32_t Fn = 1u << f;
-  const uint32_t cnt_out = (cnt_in + Fn - 1) >> f;
-  const size_t slot = (size_t)block * block_threads + thread;   // global thread slot
-  const size_t node = slot >> f;
-  const uint32_t i = (uint32_t)(slot & (Fn - 1));                // child index inside the node
-  if (node >= (size_t)W * cnt_out) return;
-  const uint32_t w = (uint32_t)(node / cnt_out), k = (uint32_t)(node % cnt_out);
-  const size_t base = slot - i;                                  // slot of child 0 of this node
-  if (phase == 0) {
-    const uint32_t child = (k << f) + i;
-    if (child < cnt_in) { S0[slot] = inA[(size_t)w * cnt_in + child]; V[slot] = inWt[(size_t)w * cnt_in + child]; }
-    else { S0[slot] = X::identity(); V[slot] = X::identity(); }
-    return;
-  }
-  if (phase <= f) {                                              // inclusive suffix scan, step 2^(phase-1)
-    const uint32_t step = 1u << (phase - 1);
-    const X* src = (phase & 1) ? S0 : S1;
-    X* dst = (phase & 1) ? S1 : S0;
-    X v = src[slot];
-    if (i + step < Fn) v = X::add(v, src[slot + step]);
-    dst[slot] = v;
-    return;
-  }
-  const X* Sfin = (f & 1) ? S1 : S0;                             // result of the last scan phase
-  if (phase <= 2 * f) {                                          // tree reduction, step 2^(2f - phase)
-    const uint32_t step = 1u << (2 * f - phase);
-    if (i < step) {
-      X a, b;
-      if (phase == f + 1) {                                      // first step reads the scan result, dropping S[0]
-        a = i ? Sfin[slot] : X::identity();
-        b = Sfin[slot + step];
-      } else {
-        a = R[slot];
-        b = R[slot + step];
-      }
-      R[slot] = X::add(a, b);
-      V[slot] = X::add(V[slot], V[slot + step]);
-    }
-    return;
-  }
-  if (i == 0) {                                                  // finish: A = S[0], Wt = sum Wt_i + 2^shift * sum_i i A_i
-    X wrel = (f == 0) ? X::identity() : R[base];
-    for (uint32_t d = 0; d < shift; d++) wrel = X::dbl(wrel);
-    outA[node] = Sfin[base];
-    outWt[node] = X::add(V[base], wrel);
-  }
-}
-
-// ---- window combine: result = sum_w 2^(c w) (Wt_w + A_w)  (single thread) ------------------------
-template <class F>
-ZKB_HDN inline void msm_horner_body(uint32_t W, uint32_t c, const XYZZ<F>* A, const XYZZ<F>* Wt, XYZZ<F>* out) {
-  XYZZ<F> acc = XYZZ<F>::identity();
-  for (uint32_t w = W; w-- > 0;) {
-    for (uint32_t d = 0; d < c; d++) acc = XYZZ<F>::dbl_ni(acc);
-    acc = XYZZ<F>::add(acc, XYZZ<F>::add(A[w], Wt[w]));
-  }
-  *out = acc;
+ZKB_HDN inline void msm_bitsum_body(uint32_t W, uint32_t cnt_in, uint32_t npend, const XYZZ<F>* inA, const XYZZ<F>* inP,
+                                    XYZZ<F>* outA, XYZZ<F>* outP, uint32_t t) {
+  const uint32_t cnt_out = cnt_in >> 3;
+  const uint32_t per_role = W * cnt_out;
+  const uint32_t role = t / per_role, node = t % per_role;
+  if (role >= 4 + npend) return;
+  const uint32_t w = node / cnt_out, k = node % cnt_out;
+  const XYZZ<F>* src = (role < 4 ? inA : inP + (size_t)(role - 4) * W * cnt_in) + (size_t)w * cnt_in + ((size_t)k << 3);
+  uint32_t mask = 0xFFu;
+  if (role == 1) mask = 0xAAu; else if (role == 2) mask = 0xCCu; else if (role == 3) mask = 0xF0u;
+  XYZZ<F> sum = XYZZ<F>::identity();
+#pragma unroll 1
+  for (uint32_t i = 0; i < 8; i++)
+    if ((mask >> i) & 1u) sum = XYZZ<F>::add(sum, src[i]);
+  XYZZ<F>* dst;
+  if (role == 0) dst = outA;
+  else if (role < 4) dst = outP + (size_t)(npend + role - 1) * per_role;
+  else dst = outP + (size_t)(role - 4) * per_role;
+  dst[node] = sum;
 }
 
 }  // namespace zkb
