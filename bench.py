@@ -11,7 +11,8 @@ witness_map (3 SpMV + 7 NTT) + 4 G1 MSM + 1 G2 MSM + final combination.
   e2e   : the same through the C-ABI call a `zokrates_b200` Rust shim makes (zkb_groth16_prove): z in pinned
           host memory, H2D of z and D2H of the window sums / proof inside the timed region
 Multi-GPU: every MSM is sharded by index range over the ranks (no data-path collective); the 5 partial
-sums per rank are all-gathered (NCCL) and rank 0 finishes the proof; witness_map is replicated.
+sums per rank are all-gathered (NCCL) and rank 0 finishes the proof; the witness map is replicated for N <= 2 and
+its three chains are computed once each and broadcast (NCCL over NVLink) for N >= 3.
 The reference arm times oracle/libzkoracle.so — the C restatement of ark's prover (the reference is
 Rust + un-vendored arkworks crates and cannot be built here) — on all host threads, on a
 bounded sample of the same circuit family.
@@ -172,6 +173,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("ZKB_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL prints its banner on stdout: keep stdout to the one JSON line
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
 
     lib = Library()
@@ -204,23 +207,32 @@ def main():
 
     last_stage = {}
 
+    # three or more ranks: the witness map's three chains are computed once each and broadcast over NVLink
+    # (zkb_groth16_prove_begin / _end, zokrates_b200/distributed.py); ZKB_WM_SHARE=0 keeps it replicated
+    share_wm = world >= 3 and os.environ.get("ZKB_WM_SHARE", "1") != "0"
+
+    def partial_step(z_arg):
+        if share_wm:
+            from zokrates_b200.distributed import prove_partial_shared_wm
+            partial = prove_partial_shared_wm(ctx, pk_h, r1cs_h, z_arg, device=torch.device("cuda", local))
+        else:
+            partial = ctx.prove_partial(pk_h, r1cs_h, z_arg)
+        last_stage.update(ctx.timings())
+        return gather_and_finish(partial)
+
     def step_resident():
         if world == 1:
             out = ctx.prove_resident(pk_h, r1cs_h, *r_s)
             last_stage.update(ctx.timings())
             return out
-        partial = ctx.prove_partial(pk_h, r1cs_h, None)
-        last_stage.update(ctx.timings())
-        return gather_and_finish(partial)
+        return partial_step(None)
 
     def step_e2e():
         if world == 1:
             out = ctx.prove(pk_h, r1cs_h, z_host, *r_s)
             last_stage.update(ctx.timings())
             return out
-        partial = ctx.prove_partial(pk_h, r1cs_h, z_host)
-        last_stage.update(ctx.timings())
-        return gather_and_finish(partial)
+        return partial_step(z_host)
 
     def barrier():
         torch.cuda.synchronize()
@@ -330,7 +342,7 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "u256-montgomery", "data": "synthetic",
             "config": {"workload": f"synthetic-r1cs-2^{args.log_n}-bn128-groth16", "constraints": n_cons, "domain": 1 << args.log_n,
                        "variables": r1cs.num_variables, "witness": args.witness, "curve": "bn128",
-                       "parallelism": f"msm-index-shard x{world}, witness_map replicated",
+                       "parallelism": f"msm-index-shard x{world} (work-balanced cuts), witness_map " + ("chains shared over NVLink" if share_wm else "replicated"),
                        "l2": f"inputs larger than L2: resident proving key {pk_bytes / 1e6:.0f} MB + sort buffers, no flush needed",
                        "timed_region": "z resident in HBM -> proof bytes on host"},
             "e2e": {"value": e2e_value, "unit": "constraints/s", "h2d_bytes_per_step": int(z.nbytes + 64),

@@ -106,6 +106,22 @@ int32_t zkb_groth16_prove_partial(zkb_ctx* ctx, uint64_t pk_handle, uint64_t r1c
 int32_t zkb_groth16_finalize(zkb_ctx* ctx, uint64_t pk_handle, const uint8_t* partials, uint32_t world,
                              const uint64_t* r, const uint64_t* s, uint8_t* proof_out, size_t proof_cap);
 
+/* Multi-GPU, shared witness map.  The three chains of ark-groth16's `witness_map` (k = 0, 1, 2:
+ * coset_fft(ifft(A z)), ...(B z), ...(C z); external crate reached from zokrates_ark/src/groth16.rs:44) are
+ * independent, so with three or more ranks each chain is computed once instead of on every rank:
+ *   zkb_groth16_prove_begin  starts the proof (z upload, the z-dependent MSMs) and computes the chains in
+ *                            `chain_mask` (bit k = chain k) into DEVICE buffers whose addresses are returned in
+ *                            chain_dev_ptrs[0..2] (`*chain_bytes` bytes each); when the mask is not 7 it returns
+ *                            after this rank's chains are complete in memory;
+ *   the host then broadcasts every chain buffer from the rank that computed it (NCCL over NVLink on the
+ *   device pointers; zokrates_b200/distributed.py) and synchronises that transfer;
+ *   zkb_groth16_prove_end    finishes the witness map, the h MSM and the reductions and returns the same
+ *                            partial blob as zkb_groth16_prove_partial (= begin with mask 7 + end). */
+int32_t zkb_groth16_prove_begin(zkb_ctx* ctx, uint64_t pk_handle, uint64_t r1cs_handle, const uint64_t* z,
+                                uint32_t chain_mask, void* chain_dev_ptrs[3], uint64_t* chain_bytes);
+int32_t zkb_groth16_prove_end(zkb_ctx* ctx, uint64_t pk_handle, uint64_t r1cs_handle, uint8_t* partial_out,
+                              size_t partial_cap);
+
 /* ---- building blocks (micro-benchmarks and parity tests; BASELINE.json config 5) ---------------
  * points: ark uncompressed affine encoding (x | y, canonical LE, infinity flag 0x40 in the last
  * byte) as in proving.key; scalars canonical LE 32 bytes; out: one point in the same encoding.

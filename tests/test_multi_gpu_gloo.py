@@ -41,9 +41,56 @@ def _worker(rank, world, port, emu_path, out_path):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 4])
 def test_sharded_prove_gloo(world, emu_lib, tmp_path):
     out = str(tmp_path / "res.npy")
     mp.spawn(_worker, args=(world, _free_port(), emu_lib.path, out), nprocs=world, join=True)
     ok, n = np.load(out)
     assert ok == 1 and n == 256
+
+
+def _worker_chains(rank, world, port, emu_path, out_path):
+    """begin/end with the chain split: every rank computes only its chains, the others arrive by broadcast.  Without the
+    exchange the result must differ on the ranks that do not own chain a (so the test cannot pass on replicated work)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from zokrates_b200 import backend, distributed, synthetic
+        from zokrates_b200._lib import Library, ZkbError
+        lib = Library(emu_path)
+        r1cs, z = synthetic.make("bn128", 1500, seed=5)          # domain 2^11: the tiled NTT path
+        ctx = backend.context("bn128", 0, lib)
+        h = ctx.r1cs_load(r1cs.num_constraints, r1cs.num_instance, r1cs.num_witness, r1cs.matrices())
+        pk = ctx.setup(h, [3, 5, 7, 11, 13, 17, 19])
+        pkh = ctx.pk_load(pk, rank, world)
+        ref = ctx.prove_partial(pkh, h, z)
+        mask = distributed.wm_chain_mask(rank, world)
+        assert mask == ({0: 1, 1: 2, 2: 4}.get(rank, 0))
+        got = distributed.prove_partial_shared_wm(ctx, pkh, h, z)
+        ok = bool(np.array_equal(ref, got))
+        ctx.prove_begin(pkh, h, z, mask)                           # no exchange this time
+        try:
+            ctx.prove_begin(pkh, h, z, mask)
+            ok = False
+        except ZkbError as e:
+            ok = ok and e.code == 1                                # "a proof is already open"
+        stale = ctx.prove_end(pkh, h)
+        # the finish step consumed buffer a: only its owner (rank 0) recomputed it, everyone else now has a wrong h
+        ok = ok and (bool(np.array_equal(stale, ref)) == (rank == 0))
+        try:
+            ctx.prove_end(pkh, h)
+            ok = False
+        except ZkbError as e:
+            ok = ok and e.code == 1                                # end without begin
+        np.save(out_path + f".{rank}.npy", np.array([ok]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [3, 4])
+def test_shared_witness_map_chains_gloo(world, emu_lib, tmp_path):
+    out = str(tmp_path / "res")
+    mp.spawn(_worker_chains, args=(world, _free_port(), emu_lib.path, out), nprocs=world, join=True)
+    for rank in range(world):
+        assert np.load(out + f".{rank}.npy")[0] == 1, f"rank {rank}"

@@ -24,9 +24,9 @@ def rows(path):
 
 
 def short(name):
-    m = re.search(r"zkb_(?:block_|phased_)?kernel<zkb::(\w+)", name)
+    m = re.search(r"zkb_(?:block_|phased_)?kernel<(?:zkb::)?(\w+)", name)
     base = m.group(1) if m else re.sub(r"\(.*", "", name)
-    if "Fp2" in name and base.startswith("k_msm"):
+    if re.search(r"msm_\w+<Fp2T?<", name) and base.startswith("k_msm"):
         base += "<G2>"
     return base[:40]
 

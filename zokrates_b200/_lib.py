@@ -24,7 +24,8 @@ SYMBOLS = [
     "zkb_pk_load", "zkb_pk_info", "zkb_pk_free", "zkb_r1cs_load", "zkb_r1cs_free", "zkb_groth16_prove",
     "zkb_r1cs_set_assignment", "zkb_groth16_prove_resident", "zkb_groth16_prove_partial", "zkb_groth16_finalize",
     "zkb_msm_g1", "zkb_msm_g2", "zkb_ntt", "zkb_witness_map", "zkb_field_op", "zkb_groth16_setup",
-    "zkb_groth16_setup_size", "zkb_last_timings", "zkb_launch_count", "zkb_peak_probe",
+    "zkb_groth16_setup_size", "zkb_last_timings", "zkb_launch_count", "zkb_peak_probe", "zkb_groth16_prove_begin",
+    "zkb_groth16_prove_end",
 ]
 
 
@@ -72,6 +73,9 @@ class Library:
         d.zkb_groth16_prove_partial.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t]
         d.zkb_groth16_finalize.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_size_t]
+        d.zkb_groth16_prove_begin.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32,
+                                              C.POINTER(C.c_void_p), _u64p]
+        d.zkb_groth16_prove_end.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t]
         d.zkb_msm_g1.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         d.zkb_msm_g2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         d.zkb_ntt.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32]
@@ -205,6 +209,22 @@ class Context:
             z = np.ascontiguousarray(z, dtype=np.uint64)
             zp = z.ctypes.data
         self.lib.check(self.lib.dll.zkb_groth16_prove_partial(self.h, pk, r1cs, zp, out.ctypes.data, len(out)))
+        return out
+
+    def prove_begin(self, pk, r1cs, z, chain_mask: int):
+        """Start a proof and compute the witness-map chains in `chain_mask`; returns ([3 device addresses], bytes each)."""
+        zp = None
+        if z is not None:
+            z = np.ascontiguousarray(z, dtype=np.uint64)
+            zp = z.ctypes.data
+        ptrs = (C.c_void_p * 3)()
+        nbytes = C.c_uint64(0)
+        self.lib.check(self.lib.dll.zkb_groth16_prove_begin(self.h, pk, r1cs, zp, chain_mask, ptrs, C.byref(nbytes)))
+        return [int(p or 0) for p in ptrs], int(nbytes.value)
+
+    def prove_end(self, pk, r1cs) -> np.ndarray:
+        out = np.zeros(self.partial_bytes, dtype=np.uint8)
+        self.lib.check(self.lib.dll.zkb_groth16_prove_end(self.h, pk, r1cs, out.ctypes.data, len(out)))
         return out
 
     def finalize(self, pk, partials: np.ndarray, world: int, r: int, s: int) -> bytes:

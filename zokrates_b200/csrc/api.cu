@@ -189,6 +189,21 @@ int32_t zkb_groth16_prove_partial(zkb_ctx* ctx, uint64_t pk, uint64_t r1cs, cons
     ctx->eng->prove_partial(pk, r1cs, z, partial_out);
   });
 }
+int32_t zkb_groth16_prove_begin(zkb_ctx* ctx, uint64_t pk, uint64_t r1cs, const uint64_t* z, uint32_t chain_mask,
+                                void* chain_dev_ptrs[3], uint64_t* chain_bytes) {
+  return guard(ctx, [&] {
+    if (!chain_dev_ptrs || !chain_bytes) throw Error(ZKB_E_ARG, "null argument");
+    ctx->eng->prove_begin(pk, r1cs, z, chain_mask, chain_dev_ptrs, chain_bytes);
+  });
+}
+int32_t zkb_groth16_prove_end(zkb_ctx* ctx, uint64_t pk, uint64_t r1cs, uint8_t* partial_out, size_t cap) {
+  return guard(ctx, [&] {
+    uint64_t sz[4];
+    ctx->eng->sizes(sz);
+    if (!partial_out || cap < sz[3]) throw Error(ZKB_E_ARG, "partial_out too small");
+    ctx->eng->prove_end(pk, r1cs, partial_out);
+  });
+}
 int32_t zkb_groth16_finalize(zkb_ctx* ctx, uint64_t pk, const uint8_t* partials, uint32_t world, const uint64_t* r,
                              const uint64_t* s, uint8_t* proof_out, size_t cap) {
   return guard(ctx, [&] {

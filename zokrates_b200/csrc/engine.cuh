@@ -495,15 +495,20 @@ class Engine : public EngineBase {
   }
 
   // h (canonical, natural order) = witness_map(z)   [device-resident]
-  void witness_map_dev(R1cs& r, StageTimer& tm) {
+  // The witness map in two halves so that several GPUs can share it (zkb_groth16_prove_begin / _end):
+  //   chains: for every k in `mask`: v_k = coset_fft(ifft(M_k z)) — three independent SpMV + 2 transforms (a, b, c)
+  //   finish: h = coset_ifft((a∘b − c) / Z)  — needs all three chains
+  void wm_chains(R1cs& r, uint32_t mask, StageTimer& tm) {
     DomainT& d = domain(r.log_n);
     const uint32_t lg = r.log_n;
     const size_t n = (size_t)1 << lg;
-    tm.begin("witness_map");
+    tm.begin("witness_map_chains");
     convert(r.z_canon.p, r.z_mont.p, 0, r.m);
     Fr* vec[3] = {r.a.p, r.b.p, r.c.p};
     const Fr* zm = r.z_mont.p;
+    const Fr* t1 = d.cos_fwd.p;
     for (int k = 0; k < 3; k++) {
+      if (!((mask >> k) & 1u)) continue;
       Fr* out = vec[k];
       const uint32_t* rp = r.rowptr[k].p;
       const uint32_t* cl = r.col[k].p;
@@ -511,14 +516,17 @@ class Engine : public EngineBase {
       const uint32_t N = (uint32_t)r.N;
       dev_zero(st_, out + r.N, (n - r.N) * FRB);
       launch<k_spmv>(st_, r.N, ZKB_LAMBDA(size_t t) { spmv_body<Fr>(rp, cl, vl, zm, out, N, (uint32_t)t); });
+      if (k == 0) d2d(st_, r.a.p + r.N, r.z_mont.p, r.ni * FRB);  // a[N + j] = z[j] for the instance variables
+      ntt_dif(out, d.tw_inv.p, lg);
+      ntt_dit(out, d.tw_fwd.p, lg, t1);   // coset shift (g^k / n at the bit-reversed position) fused into the first pass
     }
-    d2d(st_, r.a.p + r.N, r.z_mont.p, r.ni * FRB);  // a[N + j] = z[j] for the instance variables
-    const Fr* t1 = d.cos_fwd.p;
-    for (int k = 0; k < 3; k++) {
-      Fr* x = vec[k];
-      ntt_dif(x, d.tw_inv.p, lg);
-      ntt_dit(x, d.tw_fwd.p, lg, t1);   // coset shift (g^k / n at the bit-reversed position) fused into the first pass
-    }
+    tm.end();
+  }
+  void wm_finish(R1cs& r, StageTimer& tm) {
+    DomainT& d = domain(r.log_n);
+    const uint32_t lg = r.log_n;
+    const size_t n = (size_t)1 << lg;
+    tm.begin("witness_map_finish");
     Fr* pa = r.a.p; const Fr* pb = r.b.p; const Fr* pc = r.c.p;
     Fr zinv = d.zinv;
     launch<k_qap_pointwise>(st_, n, ZKB_LAMBDA(size_t t) { qap_pointwise_body<Fr>(pa, pb, pc, zinv, (uint32_t)n, (uint32_t)t); });
@@ -526,6 +534,13 @@ class Engine : public EngineBase {
     Fr* ph = r.h.p;
     const Fr* t2 = d.cos_inv.p;
     launch<k_ntt_brev>(st_, n, ZKB_LAMBDA(size_t t) { ntt_brev_copy_body<Fr>(pa, ph, t2, lg, 1, (uint32_t)t); });
+    tm.end();
+  }
+  // h (canonical, natural order) = witness_map(z)   [device-resident]
+  void witness_map_dev(R1cs& r, StageTimer& tm) {
+    tm.begin("witness_map");
+    wm_chains(r, 7, tm);
+    wm_finish(r, tm);
     tm.end();
   }
 
@@ -846,6 +861,32 @@ class Engine : public EngineBase {
     const uint64_t na = m - 1;  // pairs with assignment = z[1..]
     p->lo = na * rank / world; p->hi = na * (rank + 1) / world;
     p->hlo = hl * rank / world; p->hhi = hl * (rank + 1) / world;
+    if (world > 1 && na > 0) {
+      // The four z-MSMs share one index range per rank, but a_query / b_query are sparse (variables that never occur in
+      // A resp. B are the point at infinity and are skipped) and the sparsity is rarely uniform over the index — in the
+      // benchmark circuit 95 % of the non-infinity b points sit in the first half.  Cut the range where the WORK is
+      // equal: weight 1 (l) + 1 (a != inf) + 1 + 2.8 (b != inf: G1 and G2, G2 costs 28 / 10 of a G1 addition).
+      // Every rank derives the same cuts from the same key bytes.
+      auto is_inf = [](const uint8_t* pt, size_t bytes) { return (pt[bytes - 1] & 0x40) != 0; };
+      std::vector<float> w(na);
+      double total = 0;
+      for (uint64_t i = 0; i < na; i++) {
+        float wi = 1.0f;
+        if (!is_inf(aq + (1 + i) * G1B, G1B)) wi += 1.0f;
+        if (!is_inf(b2q + (1 + i) * G2B, G2B)) wi += 3.8f;
+        w[i] = wi;
+        total += wi;
+      }
+      auto cut = [&](uint32_t k) -> uint64_t {   // first index whose prefix weight reaches total * k / world
+        if (k == 0) return 0;
+        if (k >= world) return na;
+        const double target = total * k / world;
+        double acc = 0;
+        for (uint64_t i = 0; i < na; i++) { if (acc >= target) return i; acc += w[i]; }
+        return na;
+      };
+      p->lo = cut(rank); p->hi = cut(rank + 1);
+    }
     const uint64_t cnt = p->hi - p->lo, hcnt = p->hhi - p->hlo;
     p->a.alloc(cnt); p->b1.alloc(cnt); p->l.alloc(cnt); p->b2.alloc(cnt); p->h.alloc(hcnt);
     h2d(st_, p->a.p, aq + (1 + p->lo) * G1B, cnt * G1B);
@@ -918,13 +959,26 @@ class Engine : public EngineBase {
     return cnt && small * 2 > cnt;
   }
 
-  void prove_partial(uint64_t pkh, uint64_t rh, const uint64_t* z, uint8_t* partial_out) override {
+  // One proof's device work in two calls so that the host can exchange witness-map chains between them:
+  //   begin: upload z, start the chains of `chain_mask` on the witness-map stream, the z plan and the four z-MSMs on the
+  //          main stream; if some chains are left to other ranks, wait until this rank's chains are complete
+  //   end  : (all three chain buffers hold coset evaluations) finish the witness map, h plan, h-MSM, tails, host finish
+  // zkb_groth16_prove_partial = begin(all chains) + end.
+  std::unique_ptr<StageTimer> tm_, tm2_;
+  uint64_t open_pk_ = 0, open_r1cs_ = 0;
+  Event ev_chains_done_;
+
+  void prove_begin(uint64_t pkh, uint64_t rh, const uint64_t* z, uint32_t chain_mask, void* chain_ptrs[3],
+                   uint64_t* chain_bytes) override {
     Pk& pk = get_pk(pkh);
     R1cs& r = get_r1cs(rh);
     const size_t n = (size_t)1 << r.log_n;
     if (pk.m != r.m || pk.ni != r.ni) throw Error(ZKB_E_ARG, "proving key does not match the R1CS (variable counts)");
     if (pk.hl + 1 != n) throw Error(ZKB_E_ARG, "proving key does not match the R1CS (domain size)");
-    StageTimer tm(st_);
+    if (chain_mask > 7) throw Error(ZKB_E_ARG, "chain_mask");
+    if (open_pk_) throw Error(ZKB_E_ARG, "a proof is already open on this context (call zkb_groth16_prove_end)");
+    tm_.reset(new StageTimer(st_));
+    StageTimer& tm = *tm_;
     if (z) {
       tm.begin("h2d_z");
       h2d(st_, r.z_canon.p, z, r.m * FRB);
@@ -936,7 +990,6 @@ class Engine : public EngineBase {
     }
     const size_t slot1 = MAXW * sizeof(G1X), slot2 = MAXW * sizeof(G2X);
     d_win_.ensure(4 * slot1 + slot2);
-    G1X* w_h = (G1X*)d_win_.p;
     G1X* w_l = (G1X*)(d_win_.p + slot1);
     G1X* w_a = (G1X*)(d_win_.p + 2 * slot1);
     G1X* w_b1 = (G1X*)(d_win_.p + 3 * slot1);
@@ -949,31 +1002,53 @@ class Engine : public EngineBase {
       wm_stream_ = (e && atoi(e) == 0) ? stream_create() : stream_create_high_priority();
       has_wm_stream_ = true;
     }
-    // With one or two ranks the witness map has several milliseconds of slack (h is needed after four accumulate
-    // kernels), while the digit/sort plan of z is on the critical path and bandwidth-bound like the witness map: let the
-    // plan run alone first.  With more ranks the witness map itself is the critical path and starts at once.
-    static const int wm_early_env = getenv("ZKB_WM_EARLY") ? atoi(getenv("ZKB_WM_EARLY")) : -1;
-    const bool wm_early = wm_early_env >= 0 ? wm_early_env != 0 : pk.world > 2;
-    StageTimer tm2(wm_stream_);
-    auto enqueue_witness_map = [&]() {
+    // The witness map starts at once on its own stream.  Letting the z plan run alone first (ZKB_WM_EARLY=0) shortens the
+    // plan from 2.3 to 0.8 ms but the displaced witness-map work then slows the accumulate kernels by the same amount
+    // (measured 21.03 vs 20.97 ms, profiles/r01_tuning_log.md): the proof is work-bound, not schedule-bound.
+    static const int wm_early_env = getenv("ZKB_WM_EARLY") ? atoi(getenv("ZKB_WM_EARLY")) : 1;
+    const bool wm_early = wm_early_env != 0;
+    tm2_.reset(new StageTimer(wm_stream_));
+    StageTimer& tm2 = *tm2_;
+    auto enqueue_chains = [&]() {
       ev_z_ready_.record(st_);
       StreamScope sc(st_, wm_stream_);
       ev_z_ready_.wait(st_);
-      witness_map_dev(r, tm2);
-      tm2.begin("msm_plan_h");
-      plan_build(plan_h_, r.h.p + pk.hlo, pk.hhi - pk.hlo, 1, nullptr, pk.pre_ch);
-      tm2.end();
-      ev_h_ready_.record(st_);
+      wm_chains(r, chain_mask, tm2);
+      ev_chains_done_.record(st_);
     };
-    if (wm_early) enqueue_witness_map();
+    if (wm_early) enqueue_chains();
     tm.begin("msm_plan_z");
     plan_build(plan_z_, r.z_canon.p + 1 + pk.lo, pk.hi - pk.lo, 3, pk.skip.p, r.sparse_z ? 0 : pk.pre_cz);
     tm.end();
-    if (!wm_early) enqueue_witness_map();
+    if (!wm_early) enqueue_chains();
     msm_exec<Fq2>(plan_z_, pk.b2.p, w_b2, ws_[4], &tm, "accum1_g2_b2", 2, "tail_g2_b2");
     msm_exec<Fq>(plan_z_, pk.l.p, w_l, ws_[1], &tm, "accum1_g1_l", 0, "tail_g1_l");
     msm_exec<Fq>(plan_z_, pk.a.p, w_a, ws_[2], &tm, "accum1_g1_a", 1, "tail_g1_a");
     msm_exec<Fq>(plan_z_, pk.b1.p, w_b1, ws_[3], &tm, "accum1_g1_b1", 2, "tail_g1_b1");
+    open_pk_ = pkh; open_r1cs_ = rh;
+    if (chain_ptrs) { chain_ptrs[0] = r.a.p; chain_ptrs[1] = r.b.p; chain_ptrs[2] = r.c.p; }
+    if (chain_bytes) *chain_bytes = n * FRB;
+    // chains left to other ranks: the caller exchanges buffers next, so this rank's chains must be complete in memory
+    if (chain_mask != 7) stream_sync(wm_stream_);
+  }
+
+  void prove_end(uint64_t pkh, uint64_t rh, uint8_t* partial_out) override {
+    if (!open_pk_ || open_pk_ != pkh || open_r1cs_ != rh) throw Error(ZKB_E_ARG, "zkb_groth16_prove_end without a matching prove_begin");
+    open_pk_ = 0; open_r1cs_ = 0;
+    Pk& pk = get_pk(pkh);
+    R1cs& r = get_r1cs(rh);
+    StageTimer& tm = *tm_;
+    StageTimer& tm2 = *tm2_;
+    const size_t slot1 = MAXW * sizeof(G1X), slot2 = MAXW * sizeof(G2X);
+    G1X* w_h = (G1X*)d_win_.p;
+    {
+      StreamScope sc(st_, wm_stream_);
+      wm_finish(r, tm2);
+      tm2.begin("msm_plan_h");
+      plan_build(plan_h_, r.h.p + pk.hlo, pk.hhi - pk.hlo, 1, nullptr, pk.pre_ch);
+      tm2.end();
+      ev_h_ready_.record(st_);
+    }
     tm.begin("wait_h");
     ev_h_ready_.wait(st_);
     tm.end();
@@ -1016,6 +1091,11 @@ class Engine : public EngineBase {
     memcpy(partial_out, &hp, sizeof hp);
   }
 
+  void prove_partial(uint64_t pkh, uint64_t rh, const uint64_t* z, uint8_t* partial_out) override {
+    prove_begin(pkh, rh, z, 7, nullptr, nullptr);
+    prove_end(pkh, rh, partial_out);
+  }
+
   // the four scalar multiplications that only need (pk, r, s): computed while the GPU works
   struct FixedMults {
     HG1X rd, sd, rsd;
@@ -1026,10 +1106,12 @@ class Engine : public EngineBase {
     HFr a, b;
     memcpy(a.v, r, 32); memcpy(b.v, s, 32);
     HFr rs = HFr::mul(HFr::to_mont(a), b);  // canonical r * s
-    f.rd = HG1X::mul_affine(pk.h_fixed1[2], r, 8);
-    f.sd = HG1X::mul_affine(pk.h_fixed1[2], s, 8);
+    // four independent scalar multiplications (0.12 ms each in G1, 0.35 ms in G2): one host thread each
+    auto f_sd2 = std::async(std::launch::async, [&] { return HG2X::mul_affine(pk.h_fixed2[1], s, 8); });
+    auto f_rd = std::async(std::launch::async, [&] { return HG1X::mul_affine(pk.h_fixed1[2], r, 8); });
+    auto f_sd = std::async(std::launch::async, [&] { return HG1X::mul_affine(pk.h_fixed1[2], s, 8); });
     f.rsd = HG1X::mul_affine(pk.h_fixed1[2], (const uint32_t*)rs.v, 8);
-    f.sd2 = HG2X::mul_affine(pk.h_fixed2[1], s, 8);
+    f.rd = f_rd.get(); f.sd = f_sd.get(); f.sd2 = f_sd2.get();
     return f;
   }
 

@@ -17,6 +17,9 @@ struct EngineBase {
   virtual void r1cs_free(uint64_t h) = 0;
   virtual void set_assignment(uint64_t r1cs, const uint64_t* z) = 0;
   virtual void prove_partial(uint64_t pk, uint64_t r1cs, const uint64_t* z, uint8_t* partial_out) = 0;
+  virtual void prove_begin(uint64_t pk, uint64_t r1cs, const uint64_t* z, uint32_t chain_mask, void* chain_ptrs[3],
+                           uint64_t* chain_bytes) = 0;
+  virtual void prove_end(uint64_t pk, uint64_t r1cs, uint8_t* partial_out) = 0;
   virtual void finalize(uint64_t pk, const uint8_t* partials, uint32_t world, const uint64_t* r, const uint64_t* s,
                         uint8_t* proof_out) = 0;
   virtual void prove_full(uint64_t pk, uint64_t r1cs, const uint64_t* z, const uint64_t* r, const uint64_t* s,

@@ -4,8 +4,13 @@ The Groth16 prover's five MSMs are sums over independent (scalar, point) pairs, 
 [rank/world) slice of each query vector resident (`zkb_pk_load(rank, world)`) and produces five partial
 sums.  Elliptic-curve addition is not an NCCL reduction op, so the partial blobs (a few hundred bytes per
 rank) are all-gathered with `torch.distributed` (NCCL over NVLink on GPUs, gloo in the CPU tests) and the
-final combination runs once (rank `dst`).  witness_map is replicated: every rank needs all of h for its
-h-query slice and the transform is far cheaper than the exchange an NTT sharding would need
+final combination runs once (rank `dst`).
+
+witness_map: every rank needs all of h for its h-query slice.  With one or two ranks it is simply replicated
+(it hides under the MSM kernels).  With three or more ranks the MSM shards are so small that the replicated
+witness map becomes the critical path, and its three chains coset_fft(ifft(M z)), M = A, B, C, are independent:
+chain k is computed once, by rank k mod world, and broadcast as 32 n bytes over NVLink (`zkb_groth16_prove_begin`
+/ `_end`).  The transforms themselves stay per-GPU: sharding an NTT would need all-to-all transposes
 (SURVEY.md §8e).
 """
 from __future__ import annotations
@@ -28,6 +33,47 @@ def gather_partials(partial: np.ndarray, group=None, device=None) -> np.ndarray:
     return out.cpu().numpy()
 
 
+class _DevBuf:
+    """A device allocation owned by libzkb200 seen through __cuda_array_interface__ (torch.as_tensor shares it)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def chain_tensor(ptr: int, nbytes: int, device=None):
+    """uint8 tensor over a chain buffer returned by `zkb_groth16_prove_begin`: CUDA memory on a GPU context, host
+    memory under the host-emulation test library (device=None)."""
+    import torch
+    if device is None or str(device) == "cpu":
+        import ctypes
+        return torch.frombuffer((ctypes.c_uint8 * nbytes).from_address(ptr), dtype=torch.uint8)
+    return torch.as_tensor(_DevBuf(ptr, nbytes), device=device)
+
+
+def wm_chain_mask(rank: int, world: int) -> int:
+    """Chains this rank computes: chain k belongs to rank k mod world (all three when world < 3: replicated)."""
+    if world < 3:
+        return 7
+    return sum(1 << k for k in range(3) if k % world == rank)
+
+
+def prove_partial_shared_wm(ctx, pk_h, r1cs_h, z: Optional[np.ndarray], group=None, device=None) -> np.ndarray:
+    """This rank's partial sums with the witness map shared between the ranks (see the module docstring)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    mask = wm_chain_mask(rank, world)
+    ptrs, nbytes = ctx.prove_begin(pk_h, r1cs_h, z, mask)
+    if mask != 7:
+        for k in range(3):
+            dist.broadcast(chain_tensor(ptrs[k], nbytes, device), src=dist.get_global_rank(group, k % world) if group else k % world,
+                           group=group)
+        if device is not None and str(device) != "cpu":
+            torch.cuda.current_stream(device).synchronize()      # the chains must be in memory before prove_end reads them
+    return ctx.prove_end(pk_h, r1cs_h)
+
+
 def prove_sharded(session, z: Optional[np.ndarray], r: int, s: int, finalize_session=None, dst: int = 0, group=None,
                   device=None) -> Optional[bytes]:
     """One proof across all ranks of `group`.  `session` holds this rank's key shard; `finalize_session`
@@ -35,7 +81,10 @@ def prove_sharded(session, z: Optional[np.ndarray], r: int, s: int, finalize_ses
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    partial = session.prove_partial(z)
+    if world >= 3:
+        partial = prove_partial_shared_wm(session.ctx, session.pk_h, session.r1cs_h, z, group, device)
+    else:
+        partial = session.prove_partial(z)
     allp = gather_partials(partial, group, device)
     if rank != dst:
         return None
