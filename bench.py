@@ -212,6 +212,8 @@ def main():
     share_wm = world >= 3 and os.environ.get("ZKB_WM_SHARE", "1") != "0"
 
     def partial_step(z_arg):
+        if rank == 0:
+            ctx.finalize_prepare(pk_h, *r_s)           # r*delta1 ... s*delta2 on host threads underneath the kernels
         if share_wm:
             from zokrates_b200.distributed import prove_partial_shared_wm
             partial = prove_partial_shared_wm(ctx, pk_h, r1cs_h, z_arg, device=torch.device("cuda", local))
@@ -311,7 +313,7 @@ def main():
         alg_muls = n_pairs * 16 * 10.0                   # canonical: W = 16 windows x 10 Fq-mul per mixed add
         roofline = {"kernel": "k_msm_accum1<Fq> (h_query MSM)", "bound": "hbm", "achieved": alg_bytes / (acc_ms * 1e-3) / 1e9,
                     "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / (acc_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic,
-                    "traffic_note": "ncu dram__bytes_read+write of this kernel (profiles/r01_ncu_accum1_summary.md): the gathers go to 5 GB of "
+                    "traffic_note": "ncu dram__bytes_read+write of this kernel (profiles/r01_ncu_accum1_final.md): the gathers go to 5 GB of "
                                     "HBM-resident window tables 2^(cw)P, a deliberate bytes-for-multiplications trade (19% fewer mixed additions)",
                     "peak_source": hbm_src, "avg_launch_ms": acc_ms,
                     "note": "the kernel is integer-multiply bound, not HBM bound (230 MAD/B): see roofline_modmul"}

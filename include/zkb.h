@@ -105,6 +105,10 @@ int32_t zkb_groth16_prove_partial(zkb_ctx* ctx, uint64_t pk_handle, uint64_t r1c
                                   uint8_t* partial_out, size_t partial_cap);
 int32_t zkb_groth16_finalize(zkb_ctx* ctx, uint64_t pk_handle, const uint8_t* partials, uint32_t world,
                              const uint64_t* r, const uint64_t* s, uint8_t* proof_out, size_t proof_cap);
+/* Optional, on the rank that will call zkb_groth16_finalize: announce (r, s) before starting this rank's share so that
+ * r*delta1, s*delta1, rs*delta1 and s*delta2 (ark-groth16 create_proof_with_reduction; they need nothing from the GPU) are
+ * computed on host threads underneath the kernels.  Returns at once; finalize with the same (pk, r, s) picks them up. */
+int32_t zkb_groth16_finalize_prepare(zkb_ctx* ctx, uint64_t pk_handle, const uint64_t* r, const uint64_t* s);
 
 /* Multi-GPU, shared witness map.  The three chains of ark-groth16's `witness_map` (k = 0, 1, 2:
  * coset_fft(ifft(A z)), ...(B z), ...(C z); external crate reached from zokrates_ark/src/groth16.rs:44) are

@@ -289,19 +289,23 @@ def test_prove_begin_end_chain_exchange(gpu_lib):
     r1, z = synthetic.make("bn128", (1 << 13) - 2)
     h = ctx.r1cs_load(r1.num_constraints, r1.num_instance, r1.num_witness, r1.matrices())
     pkh = ctx.pk_load(ctx.setup(h, [3, 5, 7, 11, 1234567, 17, 19]))
-    ref = ctx.prove_partial(pkh, h, z)
+    # partial blobs hold projective points (their representation depends on the order the sort's atomics happened to
+    # produce), so results are compared as finished proofs — affine, canonical
+    fin = lambda partial: ctx.finalize(pkh, partial, 1, 111, 222)
+    ref = fin(ctx.prove_partial(pkh, h, z))
+    assert ref == ctx.prove(pkh, h, z, 111, 222)
     ptrs, nbytes = ctx.prove_begin(pkh, h, z, 7)
     assert nbytes == 32 << 13 and all(ptrs)
-    assert np.array_equal(ctx.prove_end(pkh, h), ref)
+    assert fin(ctx.prove_end(pkh, h)) == ref
     dev = torch.device("cuda", 0)
     tb, tc = chain_tensor(ptrs[1], nbytes, dev), chain_tensor(ptrs[2], nbytes, dev)
     keep_b, keep_c = tb.clone(), tc.clone()          # coset evaluations of B z and C z (the finish step only consumes a)
     tb.zero_(); tc.zero_(); torch.cuda.synchronize()
     ctx.prove_begin(pkh, h, z, 1)                    # this "rank" computes chain a only
-    assert not np.array_equal(ctx.prove_end(pkh, h), ref)
+    assert fin(ctx.prove_end(pkh, h)) != ref
     ctx.prove_begin(pkh, h, z, 1)
     tb.copy_(keep_b); tc.copy_(keep_c); torch.cuda.synchronize()
-    assert np.array_equal(ctx.prove_end(pkh, h), ref)
+    assert fin(ctx.prove_end(pkh, h)) == ref
     with pytest.raises(ZkbError):
         ctx.prove_end(pkh, h)
     ctx.close()

@@ -25,7 +25,7 @@ SYMBOLS = [
     "zkb_r1cs_set_assignment", "zkb_groth16_prove_resident", "zkb_groth16_prove_partial", "zkb_groth16_finalize",
     "zkb_msm_g1", "zkb_msm_g2", "zkb_ntt", "zkb_witness_map", "zkb_field_op", "zkb_groth16_setup",
     "zkb_groth16_setup_size", "zkb_last_timings", "zkb_launch_count", "zkb_peak_probe", "zkb_groth16_prove_begin",
-    "zkb_groth16_prove_end",
+    "zkb_groth16_prove_end", "zkb_groth16_finalize_prepare",
 ]
 
 
@@ -76,6 +76,7 @@ class Library:
         d.zkb_groth16_prove_begin.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32,
                                               C.POINTER(C.c_void_p), _u64p]
         d.zkb_groth16_prove_end.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t]
+        d.zkb_groth16_finalize_prepare.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         d.zkb_msm_g1.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         d.zkb_msm_g2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         d.zkb_ntt.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32]
@@ -226,6 +227,10 @@ class Context:
         out = np.zeros(self.partial_bytes, dtype=np.uint8)
         self.lib.check(self.lib.dll.zkb_groth16_prove_end(self.h, pk, r1cs, out.ctypes.data, len(out)))
         return out
+
+    def finalize_prepare(self, pk, r: int, s: int):
+        ra, sa = fr_array([r]), fr_array([s])
+        self.lib.check(self.lib.dll.zkb_groth16_finalize_prepare(self.h, pk, ra.ctypes.data, sa.ctypes.data))
 
     def finalize(self, pk, partials: np.ndarray, world: int, r: int, s: int) -> bytes:
         partials = np.ascontiguousarray(partials, dtype=np.uint8)

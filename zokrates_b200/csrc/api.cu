@@ -204,6 +204,12 @@ int32_t zkb_groth16_prove_end(zkb_ctx* ctx, uint64_t pk, uint64_t r1cs, uint8_t*
     ctx->eng->prove_end(pk, r1cs, partial_out);
   });
 }
+int32_t zkb_groth16_finalize_prepare(zkb_ctx* ctx, uint64_t pk, const uint64_t* r, const uint64_t* s) {
+  return guard(ctx, [&] {
+    if (!r || !s) throw Error(ZKB_E_ARG, "null argument");
+    ctx->eng->finalize_prepare(pk, r, s);
+  });
+}
 int32_t zkb_groth16_finalize(zkb_ctx* ctx, uint64_t pk, const uint8_t* partials, uint32_t world, const uint64_t* r,
                              const uint64_t* s, uint8_t* proof_out, size_t cap) {
   return guard(ctx, [&] {

@@ -202,7 +202,9 @@ inline uint32_t msm_pick_c_pre(uint64_t n, int fr_bits) {
   for (uint32_t c = 4; c <= 22; c++) {
     uint64_t W = (fr_bits + 1 + c - 1) / c;
     if (W > 64 || n * W >= (1ull << 31)) continue;
-    double cost = (double)W * 10.0 * (double)n + 40.0 * (double)(1u << (c - 1));
+    // 10 multiplications per mixed addition; a bucket costs ~70 in the reductions (segmented partial levels + bit sums,
+    // calibrated on B200: c = 19 beats c = 20 by 2 % and c = 18 by 4 % at n = 2^20, profiles/r01_tuning_log.md)
+    double cost = (double)W * 10.0 * (double)n + 70.0 * (double)(1u << (c - 1));
     if (cost < best_cost) { best_cost = cost; best = c; }
   }
   return best;
@@ -865,15 +867,15 @@ class Engine : public EngineBase {
       // The four z-MSMs share one index range per rank, but a_query / b_query are sparse (variables that never occur in
       // A resp. B are the point at infinity and are skipped) and the sparsity is rarely uniform over the index — in the
       // benchmark circuit 95 % of the non-infinity b points sit in the first half.  Cut the range where the WORK is
-      // equal: weight 1 (l) + 1 (a != inf) + 1 + 2.8 (b != inf: G1 and G2, G2 costs 28 / 10 of a G1 addition).
+      // equal: weight 1 (l) + 1.1 (a != inf) + 4.5 (b != inf: G1 and G2; a G2 addition is 28 / 10 of a G1 addition and runs less efficiently).
       // Every rank derives the same cuts from the same key bytes.
       auto is_inf = [](const uint8_t* pt, size_t bytes) { return (pt[bytes - 1] & 0x40) != 0; };
       std::vector<float> w(na);
       double total = 0;
       for (uint64_t i = 0; i < na; i++) {
         float wi = 1.0f;
-        if (!is_inf(aq + (1 + i) * G1B, G1B)) wi += 1.0f;
-        if (!is_inf(b2q + (1 + i) * G2B, G2B)) wi += 3.8f;
+        if (!is_inf(aq + (1 + i) * G1B, G1B)) wi += 1.1f;    // measured per-point times relative to l (single GPU, 2^20)
+        if (!is_inf(b2q + (1 + i) * G2B, G2B)) wi += 4.5f;
         w[i] = wi;
         total += wi;
       }
@@ -936,7 +938,10 @@ class Engine : public EngineBase {
     Pk& p = get_pk(h);
     out[0] = p.ni; out[1] = p.m; out[2] = p.hl; out[3] = p.ll;
   }
-  void pk_free(uint64_t h) override { pks_.erase(h); }
+  void pk_free(uint64_t h) override {
+    if (prepared_.pk == h) { if (prepared_.fut.valid()) prepared_.fut.wait(); prepared_.pk = 0; }
+    pks_.erase(h);
+  }
 
   // ------------------------------------------------------------------------------ prove
   MsmPlan plan_z_, plan_h_;
@@ -1146,11 +1151,34 @@ class Engine : public EngineBase {
     put(0, pa.x); put(1, pa.y); put(2, pb.x.c0); put(3, pb.x.c1); put(4, pb.y.c0); put(5, pb.y.c1); put(6, pc.x); put(7, pc.y);
   }
 
+  // Multi-GPU: the rank that will finalize may announce (pk, r, s) before it starts its own share of the proof; the four
+  // scalar multiplications that depend on nothing else then run on host threads underneath the GPU work.
+  struct Prepared {
+    uint64_t pk = 0;
+    uint32_t r[8], s[8];
+    std::future<FixedMults> fut;
+  } prepared_;
+  void finalize_prepare(uint64_t pkh, const uint64_t* r, const uint64_t* s) override {
+    Pk& pk = get_pk(pkh);
+    if (prepared_.pk && prepared_.fut.valid()) prepared_.fut.wait();
+    prepared_.pk = pkh;
+    memcpy(prepared_.r, r, 32); memcpy(prepared_.s, s, 32);
+    const Pk* pkp = &pk;
+    const uint32_t* rr = prepared_.r; const uint32_t* ss = prepared_.s;
+    prepared_.fut = std::async(std::launch::async, [pkp, rr, ss] { return fixed_mults(*pkp, rr, ss); });
+  }
+
   void finalize(uint64_t pkh, const uint8_t* partials, uint32_t world, const uint64_t* r, const uint64_t* s,
                 uint8_t* proof_out) override {
     Pk& pk = get_pk(pkh);
     if (world == 0) throw Error(ZKB_E_ARG, "world");
-    FixedMults fm = fixed_mults(pk, (const uint32_t*)r, (const uint32_t*)s);
+    FixedMults fm;
+    if (prepared_.pk == pkh && prepared_.fut.valid() && !memcmp(prepared_.r, r, 32) && !memcmp(prepared_.s, s, 32)) {
+      fm = prepared_.fut.get();
+      prepared_.pk = 0;
+    } else {
+      fm = fixed_mults(pk, (const uint32_t*)r, (const uint32_t*)s);
+    }
     finalize_with(pk, fm, partials, world, (const uint32_t*)r, (const uint32_t*)s, proof_out);
   }
 

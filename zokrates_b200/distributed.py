@@ -81,6 +81,8 @@ def prove_sharded(session, z: Optional[np.ndarray], r: int, s: int, finalize_ses
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
+    if rank == dst:
+        (finalize_session or session).ctx.finalize_prepare((finalize_session or session).pk_h, r, s)
     if world >= 3:
         partial = prove_partial_shared_wm(session.ctx, session.pk_h, session.r1cs_h, z, group, device)
     else:
