@@ -126,6 +126,22 @@ int32_t zkb_groth16_prove_begin(zkb_ctx* ctx, uint64_t pk_handle, uint64_t r1cs_
 int32_t zkb_groth16_prove_end(zkb_ctx* ctx, uint64_t pk_handle, uint64_t r1cs_handle, uint8_t* partial_out,
                               size_t partial_cap);
 
+/* ---- witness side -------------------------------------------------
+ * zkb_r1cs_check: (A z) o (B z) == C z for every constraint, on the device; z = NULL checks the resident assignment.
+ *   Returns ZKB_E_UNSAT and the first violated constraint index (the interpreter's `UnsatisfiedConstraint`,
+ *   zokrates_interpreter/src/lib.rs:95-104), ZKB_OK and UINT64_MAX otherwise.
+ * zkb_witness_eval: witness generation for constraint-defined programs by dependency levels, following the rule of
+ *   `Interpreter::execute_with_log_stream` (zokrates_interpreter/src/lib.rs:61-138): a constraint whose linear side is one
+ *   fresh variable with coefficient one assigns it the value of the quadratic side, any other constraint is checked.
+ *   z_inout: m x 32 bytes canonical LE, inputs (and `~one`) filled in, in the column order of zkb_r1cs_load; level l owns
+ *   entries [level_ptr[l], level_ptr[l+1]) of rows[] (constraint indices) / out_var[] (assigned column or 0xFFFFFFFF = check).
+ *   Directives (solvers) have no device path: the host interpreter handles programs that use them.  The finished
+ *   assignment is written back and stays resident for zkb_groth16_prove_resident. */
+int32_t zkb_r1cs_check(zkb_ctx* ctx, uint64_t r1cs_handle, const uint64_t* z, uint64_t* first_unsatisfied);
+int32_t zkb_witness_eval(zkb_ctx* ctx, uint64_t r1cs_handle, uint64_t* z_inout, uint32_t n_levels,
+                         const uint32_t* level_ptr, const uint32_t* rows, const uint32_t* out_var,
+                         uint64_t* first_unsatisfied);
+
 /* ---- building blocks (micro-benchmarks and parity tests; BASELINE.json config 5) ---------------
  * points: ark uncompressed affine encoding (x | y, canonical LE, infinity flag 0x40 in the last
  * byte) as in proving.key; scalars canonical LE 32 bytes; out: one point in the same encoding.

@@ -25,7 +25,7 @@ SYMBOLS = [
     "zkb_r1cs_set_assignment", "zkb_groth16_prove_resident", "zkb_groth16_prove_partial", "zkb_groth16_finalize",
     "zkb_msm_g1", "zkb_msm_g2", "zkb_ntt", "zkb_witness_map", "zkb_field_op", "zkb_groth16_setup",
     "zkb_groth16_setup_size", "zkb_last_timings", "zkb_launch_count", "zkb_peak_probe", "zkb_groth16_prove_begin",
-    "zkb_groth16_prove_end", "zkb_groth16_finalize_prepare",
+    "zkb_groth16_prove_end", "zkb_groth16_finalize_prepare", "zkb_r1cs_check", "zkb_witness_eval",
 ]
 
 
@@ -77,6 +77,8 @@ class Library:
                                               C.POINTER(C.c_void_p), _u64p]
         d.zkb_groth16_prove_end.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t]
         d.zkb_groth16_finalize_prepare.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        d.zkb_r1cs_check.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, _u64p]
+        d.zkb_witness_eval.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, _u64p]
         d.zkb_msm_g1.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         d.zkb_msm_g2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         d.zkb_ntt.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32]
@@ -240,6 +242,31 @@ class Context:
         self.lib.check(self.lib.dll.zkb_groth16_finalize(self.h, pk, partials.ctypes.data, world, ra.ctypes.data,
                                                          sa.ctypes.data, out.ctypes.data, len(out)))
         return out.tobytes()
+
+    # -- witness side
+    def r1cs_check(self, r1cs, z=None):
+        """None if (A z) o (B z) == C z; else the index of the first violated constraint (status ZKB_E_UNSAT)."""
+        zp = None
+        if z is not None:
+            z = np.ascontiguousarray(z, dtype=np.uint64)
+            zp = z.ctypes.data
+        first = C.c_uint64(0)
+        st = self.lib.dll.zkb_r1cs_check(self.h, r1cs, zp, C.byref(first))
+        if st == 5:
+            return int(first.value)
+        self.lib.check(st)
+        return None
+
+    def witness_eval(self, r1cs, z: np.ndarray, level_ptr, rows, out_var) -> np.ndarray:
+        """Fill the assignment level by level on the device; raises ZkbError(ZKB_E_UNSAT) if a checked constraint fails."""
+        z = np.ascontiguousarray(z, dtype=np.uint64).copy()
+        level_ptr = np.ascontiguousarray(level_ptr, dtype=np.uint32)
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        out_var = np.ascontiguousarray(out_var, dtype=np.uint32)
+        first = C.c_uint64(0)
+        self.lib.check(self.lib.dll.zkb_witness_eval(self.h, r1cs, z.ctypes.data, len(level_ptr) - 1, level_ptr.ctypes.data,
+                                                     rows.ctypes.data, out_var.ctypes.data, C.byref(first)))
+        return z
 
     # -- building blocks
     def msm(self, group: int, points: bytes, scalars: np.ndarray) -> bytes:

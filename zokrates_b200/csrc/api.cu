@@ -238,6 +238,22 @@ int32_t zkb_ntt(zkb_ctx* ctx, uint64_t* data, uint32_t log_n, int32_t inverse, i
 int32_t zkb_witness_map(zkb_ctx* ctx, uint64_t r1cs, const uint64_t* z, uint64_t* h_out, uint64_t cap) {
   return guard(ctx, [&] { if (!z || !h_out) throw Error(ZKB_E_ARG, "null"); ctx->eng->witness_map(r1cs, z, h_out, cap); });
 }
+int32_t zkb_r1cs_check(zkb_ctx* ctx, uint64_t r1cs, const uint64_t* z, uint64_t* first_unsatisfied) {
+  return guard(ctx, [&] {
+    uint64_t f = ctx->eng->witness_eval(r1cs, const_cast<uint64_t*>(z), 0, nullptr, nullptr, nullptr);
+    if (first_unsatisfied) *first_unsatisfied = f;
+    if (f != ~0ull) throw Error(ZKB_E_UNSAT, "constraint " + std::to_string(f) + " is not satisfied");
+  });
+}
+int32_t zkb_witness_eval(zkb_ctx* ctx, uint64_t r1cs, uint64_t* z_inout, uint32_t n_levels, const uint32_t* level_ptr,
+                         const uint32_t* rows, const uint32_t* out_var, uint64_t* first_unsatisfied) {
+  return guard(ctx, [&] {
+    if (!z_inout || !n_levels) throw Error(ZKB_E_ARG, "null argument");
+    uint64_t f = ctx->eng->witness_eval(r1cs, z_inout, n_levels, level_ptr, rows, out_var);
+    if (first_unsatisfied) *first_unsatisfied = f;
+    if (f != ~0ull) throw Error(ZKB_E_UNSAT, "constraint " + std::to_string(f) + " is not satisfied");
+  });
+}
 int32_t zkb_field_op(zkb_ctx* ctx, int32_t field, int32_t op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n) {
   return guard(ctx, [&] {
     if (!a || !out) throw Error(ZKB_E_ARG, "null argument");

@@ -30,7 +30,7 @@ struct k_fr_convert; struct k_spmv; struct k_ntt_dif; struct k_ntt_dit; struct k
 struct k_ntt_table; struct k_qap_pointwise; struct k_msm_digits; struct k_msm_scatter; struct k_msm_accum1;
 struct k_msm_accum2; struct k_msm_bitsum; struct k_pk_convert; struct k_final_a; struct k_final_b;
 struct k_final_c; struct k_final_d; struct k_point_out; struct k_field_op; struct k_setup_scalars; struct k_fixed_base;
-struct k_to_affine; struct k_copy; struct k_msm_table; struct k_ntt_dif_tile; struct k_ntt_dit_tile;
+struct k_to_affine; struct k_copy; struct k_msm_table; struct k_ntt_dif_tile; struct k_ntt_dit_tile; struct k_witness_level;
 
 // ---------------------------------------------------------------------------------------------
 // stage timer: CUDA events on the engine stream (no-op in the host emulation)
@@ -556,6 +556,62 @@ class Engine : public EngineBase {
     d2h(st_, h_out, r.h.p, n * FRB);
     stream_sync(st_);
     tm.collect(timings);
+  }
+
+  // Witness evaluation by dependency levels and the R1CS satisfaction check (ntt.cuh::witness_level_body).
+  // z_io: canonical assignment, inputs filled in, m x 32 bytes (nullptr: check the resident assignment);
+  // level_ptr[n_levels + 1] indexes rows / out_var (column assigned by that row or WIT_CHECK).  n_levels == 0: check all rows.
+  // The finished assignment stays resident (zkb_groth16_prove_resident can follow).  Returns the first unsatisfied row or ~0.
+  uint64_t witness_eval(uint64_t rh, uint64_t* z_io, uint32_t n_levels, const uint32_t* level_ptr, const uint32_t* rows,
+                        const uint32_t* out_var) override {
+    R1cs& r = get_r1cs(rh);
+    StageTimer tm(st_);
+    if (z_io) h2d(st_, r.z_canon.p, z_io, r.m * FRB);
+    else if (!r.has_z) throw Error(ZKB_E_ARG, "no resident assignment");
+    DevBuf<uint32_t> d_rows, d_out, d_flag(1);
+    dev_fill_ff(st_, d_flag.p, 4);
+    tm.begin("witness_eval");
+    convert(r.z_canon.p, r.z_mont.p, 0, r.m);
+    const uint32_t* rpA = r.rowptr[0].p; const uint32_t* clA = r.col[0].p; const Fr* vlA = r.val[0].p;
+    const uint32_t* rpB = r.rowptr[1].p; const uint32_t* clB = r.col[1].p; const Fr* vlB = r.val[1].p;
+    const uint32_t* rpC = r.rowptr[2].p; const uint32_t* clC = r.col[2].p; const Fr* vlC = r.val[2].p;
+    Fr* zm = r.z_mont.p;
+    uint32_t* flag = d_flag.p;
+    if (n_levels == 0) {
+      const uint32_t* nul = nullptr;
+      const uint32_t N = (uint32_t)r.N;
+      launch<k_witness_level>(st_, r.N, ZKB_LAMBDA(size_t t) {
+        witness_level_body<Fr>(rpA, clA, vlA, rpB, clB, vlB, rpC, clC, vlC, zm, nul, nul, 0, N, flag, (uint32_t)t);
+      });
+    } else {
+      if (!level_ptr || !rows || !out_var) throw Error(ZKB_E_ARG, "null level description");
+      const uint32_t total = level_ptr[n_levels];
+      for (uint32_t l = 0; l < n_levels; l++)
+        if (level_ptr[l] > level_ptr[l + 1] || level_ptr[l + 1] > total) throw Error(ZKB_E_ARG, "bad level_ptr");
+      for (uint32_t i = 0; i < total; i++)
+        if (rows[i] >= r.N || (out_var[i] != WIT_CHECK && out_var[i] >= r.m)) throw Error(ZKB_E_ARG, "row / variable index out of range");
+      d_rows.alloc(total ? total : 1); d_out.alloc(total ? total : 1);
+      h2d(st_, d_rows.p, rows, (size_t)total * 4);
+      h2d(st_, d_out.p, out_var, (size_t)total * 4);
+      const uint32_t* pr = d_rows.p; const uint32_t* po = d_out.p;
+      for (uint32_t l = 0; l < n_levels; l++) {
+        const uint32_t lo = level_ptr[l], hi = level_ptr[l + 1];
+        launch<k_witness_level>(st_, hi - lo, ZKB_LAMBDA(size_t t) {
+          witness_level_body<Fr>(rpA, clA, vlA, rpB, clB, vlB, rpC, clC, vlC, zm, pr, po, lo, hi, flag, (uint32_t)t);
+        });
+      }
+      convert(r.z_mont.p, r.z_canon.p, 1, r.m);
+    }
+    tm.end();
+    uint32_t first = 0;
+    d2h(st_, &first, d_flag.p, 4);
+    if (z_io && n_levels) d2h(st_, z_io, r.z_canon.p, r.m * FRB);
+    stream_sync(st_);
+    tm.collect(timings);
+    if (z_io || n_levels) { r.has_z = true; }
+    if (z_io && n_levels) r.sparse_z = assignment_is_sparse(z_io, r.m);
+    else if (z_io) r.sparse_z = assignment_is_sparse(z_io, r.m);
+    return first == 0xFFFFFFFFu ? ~0ull : (uint64_t)first;
   }
 
   // ------------------------------------------------------------------------------ MSM

@@ -28,6 +28,8 @@ struct EngineBase {
   virtual void msm(int group, const uint8_t* points, const uint64_t* scalars, uint64_t n, uint8_t* out) = 0;
   virtual void ntt(uint64_t* data, uint32_t log_n, int inverse, int coset) = 0;
   virtual void witness_map(uint64_t r1cs, const uint64_t* z, uint64_t* h_out, uint64_t cap) = 0;
+  virtual uint64_t witness_eval(uint64_t r1cs, uint64_t* z_io, uint32_t n_levels, const uint32_t* level_ptr,
+                                const uint32_t* rows, const uint32_t* out_var) = 0;
   virtual void field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n) = 0;
   virtual size_t setup_size(uint64_t r1cs) = 0;
   virtual void setup(uint64_t r1cs, const uint64_t* trapdoor7, uint8_t* pk_out, size_t cap, size_t* len) = 0;

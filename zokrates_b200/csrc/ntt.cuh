@@ -267,4 +267,39 @@ ZKB_HDN inline void spmv_body(const uint32_t* rowptr, const uint32_t* col, const
   out[t] = acc;
 }
 
+
+// ---- levelised witness evaluation / R1CS satisfaction check ------------------------------------------------
+// Restates the per-statement rule of zokrates_interpreter/src/lib.rs:61-138 on the R1CS rows: a constraint whose linear side
+// is one fresh variable with coefficient one ASSIGNS it the value of the quadratic side, every other constraint is CHECKED
+// (`Error::UnsatisfiedConstraint`).  The statements of one dependency level are independent: one thread each.
+// rows == nullptr: row = index (check of the whole system); out_var == nullptr: every row is a check.
+static constexpr uint32_t WIT_CHECK = 0xFFFFFFFFu;
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void zkb_atomic_min(uint32_t* p, uint32_t v) { atomicMin(p, v); }
+#else
+inline void zkb_atomic_min(uint32_t* p, uint32_t v) { if (v < *p) *p = v; }
+#endif
+template <class Fr>
+ZKB_HDN inline Fr csr_row_dot(const uint32_t* rowptr, const uint32_t* col, const Fr* val, const Fr* z, uint32_t row) {
+  Fr acc = Fr::zero();
+  for (uint32_t k = rowptr[row]; k < rowptr[row + 1]; k++) acc = Fr::add(acc, Fr::mul(val[k], z[col[k]]));
+  return acc;
+}
+template <class Fr>
+ZKB_HDN inline void witness_level_body(const uint32_t* rpA, const uint32_t* clA, const Fr* vlA, const uint32_t* rpB,
+                                       const uint32_t* clB, const Fr* vlB, const uint32_t* rpC, const uint32_t* clC,
+                                       const Fr* vlC, Fr* z, const uint32_t* rows, const uint32_t* out_var, uint32_t lo,
+                                       uint32_t hi, uint32_t* first_unsat, uint32_t t) {
+  const uint32_t i = lo + t;
+  if (i >= hi) return;
+  const uint32_t row = rows ? rows[i] : i;
+  const Fr q = Fr::mul(csr_row_dot<Fr>(rpA, clA, vlA, z, row), csr_row_dot<Fr>(rpB, clB, vlB, z, row));
+  const uint32_t ov = out_var ? out_var[i] : WIT_CHECK;
+  if (ov != WIT_CHECK) {
+    z[ov] = q;
+  } else if (!(q == csr_row_dot<Fr>(rpC, clC, vlC, z, row))) {
+    zkb_atomic_min(first_unsat, row);
+  }
+}
+
 }  // namespace zkb

@@ -1,0 +1,94 @@
+"""Witness generation on the GPU for constraint-defined programs (SURVEY.md §8 rows a9–a11).
+
+`zokrates compute-witness` runs `Interpreter::execute_with_log_stream`
+(/root/reference/zokrates_interpreter/src/lib.rs:61-138) statement by statement: a constraint whose linear side is one
+variable with coefficient one that has no value yet ASSIGNS it the value of the quadratic side, every other constraint is
+CHECKED (`Error::UnsatisfiedConstraint`), directives call a solver.  The assignments form a dependency DAG; all statements
+of one depth are independent, so the device evaluates the program level by level (`zkb_witness_eval`, one thread per
+statement).  This module does the host part: it derives the levels from the R1CS rows (same rule, same statement order
+for ties) and maps the result back to `ir.Witness`.  Directives have no device path — programs that use solvers stay with
+`ir.Interpreter`, as they stay on the host in the reference.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ._lib import fr_array, fr_from_array
+from .curves import curve as _curve
+from .ir import Constraint, Directive, Prog, UnsatisfiedConstraint, Variable, Witness
+from .r1cs import R1CS, synthesize
+
+CHECK = 0xFFFFFFFF
+
+
+def levelize(r1cs: R1CS, defined_cols: Iterable[int]) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """(level_ptr, rows, out_var) for `zkb_witness_eval`.  `defined_cols`: columns that hold values before the first
+    statement runs (the constant one and the program arguments)."""
+    (ap, ac, _), (bp, bc, _), (cp, cc, cv) = r1cs.a, r1cs.b, r1cs.c
+    m, N = r1cs.num_variables, r1cs.num_constraints
+    level = np.full(m, -1, dtype=np.int64)
+    for c in defined_cols:
+        level[c] = 0
+    row_level = np.zeros(N, dtype=np.int64)
+    out_var = np.full(N, CHECK, dtype=np.uint32)
+    one = np.array([1, 0, 0, 0], dtype=np.uint64)
+    for k in range(N):
+        quad = np.concatenate([ac[int(ap[k]):int(ap[k + 1])], bc[int(bp[k]):int(bp[k + 1])]])
+        lin = cc[int(cp[k]):int(cp[k + 1])]
+        if quad.size and level[quad].min() < 0:
+            raise KeyError(f"constraint {k} reads a variable that has no value yet")
+        base = int(level[quad].max()) if quad.size else 0
+        if lin.size == 1 and level[lin[0]] < 0 and np.array_equal(cv[int(cp[k])], one):
+            out_var[k] = lin[0]
+            row_level[k] = base + 1
+            level[lin[0]] = base + 1
+        else:
+            if lin.size and level[lin].min() < 0:
+                raise KeyError(f"constraint {k} reads a variable that has no value yet")
+            row_level[k] = max(base, int(level[lin].max()) if lin.size else 0) + 1
+    order = np.argsort(row_level, kind="stable").astype(np.uint32)
+    n_levels = int(row_level.max()) if N else 0
+    counts = np.bincount(row_level, minlength=n_levels + 1)[1:]
+    level_ptr = np.zeros(n_levels + 1, dtype=np.uint32)
+    np.cumsum(counts, out=level_ptr[1:])
+    return level_ptr, order, out_var[order]
+
+
+def generate_witness(prog: Prog, inputs: Sequence[int], ctx=None, lib=None) -> Witness:
+    """`Interpreter::execute` for a directive-free program, evaluated on the device.  Same result as `ir.Interpreter`
+    (every variable of the constraint system gets its value) and the same failures: wrong input count, unsatisfied
+    constraint."""
+    from . import backend
+    c = _curve(prog.curve)
+    if len(inputs) != len(prog.arguments):
+        raise ValueError(f"WrongInputCount: expected {len(prog.arguments)}, received {len(inputs)}")
+    if any(isinstance(s, Directive) for s in prog.statements):
+        raise NotImplementedError("solver directives have no device path: use ir.Interpreter")
+    r1cs = synthesize(prog)
+    cols = {v: i for i, v in enumerate(r1cs.instance_vars)}
+    cols.update({v: r1cs.num_instance + i for i, v in enumerate(r1cs.witness_vars)})
+    vals = [0] * r1cs.num_variables
+    vals[0] = 1
+    for p, x in zip(prog.arguments, inputs):
+        vals[cols[p.id]] = int(x) % c.r
+    level_ptr, rows, out_var = levelize(r1cs, [0] + [cols[p.id] for p in prog.arguments])
+    ctx = ctx or backend.context(c, 0, lib)
+    h = ctx.r1cs_load(r1cs.num_constraints, r1cs.num_instance, r1cs.num_witness, r1cs.matrices())
+    try:
+        if len(level_ptr) > 1:
+            from ._lib import ZkbError
+            try:
+                z = ctx.witness_eval(h, fr_array(vals), level_ptr, rows, out_var)
+            except ZkbError as e:
+                if e.code == 5:
+                    raise UnsatisfiedConstraint(str(e))
+                raise
+            vals = fr_from_array(z)
+    finally:
+        ctx.r1cs_free(h)
+    w = Witness(curve=c)
+    for v, col in cols.items():
+        w.insert(v, vals[col])
+    return w
