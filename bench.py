@@ -161,6 +161,11 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE line (the JSON): libraries that print on fd 1 (NCCL's version banner, whatever
+    # NCCL_DEBUG / nccl.conf say) go to stderr for the duration of the run
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -357,7 +362,10 @@ def main():
             "stages_ms": stage_res,
             "prep_s": round(prep_s, 1),
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 

@@ -196,12 +196,12 @@ inline uint32_t msm_pick_c(uint64_t n, int fr_bits) {
 }
 
 // with precomputed window multiples all windows share one bucket set, so larger windows pay off
-inline uint32_t msm_pick_c_pre(uint64_t n, int fr_bits) {
-  uint32_t best = 4;
+inline uint32_t msm_pick_c_pre(uint64_t n, int fr_bits, uint64_t max_w = 16 /* msm_table_body keeps W multiples per thread */) {
+  uint32_t best = 0;
   double best_cost = 1e300;
   for (uint32_t c = 4; c <= 22; c++) {
     uint64_t W = (fr_bits + 1 + c - 1) / c;
-    if (W > 64 || n * W >= (1ull << 31)) continue;
+    if (W > max_w || n * W >= (1ull << 31)) continue;
     // 10 multiplications per mixed addition; a bucket costs ~70 in the reductions (segmented partial levels + bit sums,
     // calibrated on B200: c = 19 beats c = 20 by 2 % and c = 18 by 4 % at n = 2^20, profiles/r01_tuning_log.md)
     double cost = (double)W * 10.0 * (double)n + 70.0 * (double)(1u << (c - 1));
@@ -778,9 +778,7 @@ class Engine : public EngineBase {
     const uint32_t W = pl.sh.pre ? 1 : pl.sh.W, cnt = ws.tree_cnt, L = ws.tree_lvls, c = pl.sh.c;
     const size_t nodes = (size_t)W * cnt;
     const HX* A = slot;
-    HX acc = HX::identity();
-    for (uint32_t w = W; w-- > 0;) {
-      for (uint32_t d = 0; d < c; d++) acc = HX::dbl(acc);
+    auto window_sum = [&](uint32_t w) {
       HX run = HX::identity(), hi = HX::identity();
       for (uint32_t k = cnt; k-- > 0;) {
         run = HX::add(run, A[(size_t)w * cnt + k]);
@@ -792,7 +790,22 @@ class Engine : public EngineBase {
         for (uint32_t k = 0; k < cnt; k++) sb = HX::add(sb, P[k]);
         hi = HX::add(HX::dbl(hi), sb);
       }
-      acc = HX::add(acc, HX::add(hi, run));   // bucket j holds weight j + 1
+      return HX::add(hi, run);   // bucket j holds weight j + 1
+    };
+    std::vector<HX> S(W);
+    if (W >= 8) {   // window mode (sparse witnesses, small MSMs): the per-window sums are independent, four host threads
+      auto part = [&](uint32_t q) { for (uint32_t w = q; w < W; w += 4) S[w] = window_sum(w); };
+      std::future<void> f1 = std::async(std::launch::async, part, 1u), f2 = std::async(std::launch::async, part, 2u),
+                        f3 = std::async(std::launch::async, part, 3u);
+      part(0);
+      f1.get(); f2.get(); f3.get();
+    } else {
+      for (uint32_t w = 0; w < W; w++) S[w] = window_sum(w);
+    }
+    HX acc = HX::identity();
+    for (uint32_t w = W; w-- > 0;) {
+      if (w + 1 < W) for (uint32_t d = 0; d < c; d++) acc = HX::dbl(acc);
+      acc = HX::add(acc, S[w]);
     }
     return acc;
   }
@@ -857,7 +870,9 @@ class Engine : public EngineBase {
       const char* emin = getenv("ZKB_PRECOMP_MIN");   // test hooks: minimum size / forced window width
       const char* ec = getenv("ZKB_PRECOMP_C");
       if (n < (uint64_t)(emin ? atoll(emin) : (1 << 14))) return;   // small MSMs are latency-bound; tables buy nothing
+      // the search is restricted to W <= 16 (an 8-way shard of 2^20 would otherwise pick c = 15, W = 17 and lose the tables)
       uint32_t cc = ec ? (uint32_t)atoi(ec) : msm_pick_c_pre(n, C::FR_BITS);
+      if (cc == 0) return;
       uint32_t ww = (C::FR_BITS + 1 + cc - 1) / cc;
       if (ww > 16) return;
       c = cc; W = ww;
