@@ -114,3 +114,45 @@ def test_rejections():
     d[k:k + 32] = b"\xff" * 32                                # coefficient >= modulus
     with pytest.raises(zir.ZirFormatError, match="non-canonical"):
         zir.read_prog(bytes(d))
+
+
+def test_file_level_pipeline_on_the_emulated_engine(tmp_path, emu_lib, monkeypatch):
+    """`out` + arguments -> zkb-compute-witness -> `witness` (-> .json, .wtns) -> zkb-generate-proof -> `proof.json`, the two
+    file-level tools chained like `zokrates compute-witness` / `generate-proof`; kernels run in the host-emulation library
+    (ZKB200_LIB), results compared with the host interpreter and the python oracle's proof."""
+    import io, json
+    from oracle import ark, ir as oir
+    from oracle.ff import BN254
+    from tools import zkb_compute_witness, zkb_generate_proof
+    from zokrates_b200 import _lib, backend, circom
+    monkeypatch.setenv("ZKB200_LIB", emu_lib.path)
+    monkeypatch.setattr(_lib, "_default", None)
+    monkeypatch.setattr(backend, "_contexts", {})
+    a_, b_ = Variable.new(0), Variable.new(1)
+    prog = Prog([Parameter.private_(a_), Parameter.public(b_)], 0, [ir.constraint(a_, a_, b_)], "bn128")
+    (tmp_path / "out").write_bytes(zir.write_prog(prog))
+    rc = zkb_compute_witness.main(["-i", str(tmp_path / "out"), "-o", str(tmp_path / "witness"), "-a", "337", "113569", "--json",
+                                   "--circom-witness", str(tmp_path / "out.wtns")])
+    assert rc == 0
+    ref = ir.Interpreter().execute(prog, [337, 113569])
+    assert (tmp_path / "witness").read_bytes() == ref.write()
+    assert (tmp_path / "witness.json").read_text() == ref.write_json()
+    assert (tmp_path / "out.wtns").read_bytes() == circom.write_witness(ref, [b_])
+    with pytest.raises(SystemExit, match="Execution failed"):
+        zkb_compute_witness.main(["-i", str(tmp_path / "out"), "-o", str(tmp_path / "w2"), "-a", "3", "10"])
+    with pytest.raises(SystemExit, match="Could not parse argument"):
+        zkb_compute_witness.main(["-i", str(tmp_path / "out"), "-o", str(tmp_path / "w2"), "-a", "x"])
+    td = [11, 22, 33, 44, 55555, 3, 7]
+    kp = backend.B200.setup(prog, td)
+    (tmp_path / "proving.key").write_bytes(kp.pk)
+    rc = zkb_generate_proof.main(["-i", str(tmp_path / "out"), "-w", str(tmp_path / "witness"), "-p", str(tmp_path / "proving.key"),
+                                  "-j", str(tmp_path / "proof.json"), "-e", "pipeline"])
+    assert rc == 0
+    c = BN254
+    oprog = oir.Prog([(a_.id, True), (b_.id, False)], 0, [oir.Constraint([(a_.id, 1)], [(a_.id, 1)], [(b_.id, 1)])])
+    ow = oir.execute(c, oprog, [337, 113569])
+    r1cs_o, z = ark.synthesize(oprog, ow)
+    orng = ark.rng_from_entropy("pipeline")
+    r, s = ark.fr_rand(c, orng), ark.fr_rand(c, orng)
+    exp = ark.trapdoor_expected_proof(c, r1cs_o, ark.Trapdoor(*td), z, r, s)
+    assert (tmp_path / "proof.json").read_text() == ark.tagged_proof_json(c, exp, [113569])
