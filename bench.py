@@ -351,7 +351,10 @@ def main():
                        "variables": r1cs.num_variables, "witness": args.witness, "curve": "bn128",
                        "parallelism": f"msm-index-shard x{world} (work-balanced cuts), witness_map " + ("chains shared over NVLink" if share_wm else "replicated"),
                        "l2": f"inputs larger than L2: resident proving key {pk_bytes / 1e6:.0f} MB + sort buffers, no flush needed",
-                       "timed_region": "z resident in HBM -> proof bytes on host"},
+                       "timed_region": "z resident in HBM -> proof bytes on host",
+                       "timing": "K proofs bracketed by barrier + synchronize; every proof ends in a stream synchronize inside the library, so "
+                                 "the host clock equals the device time of the critical path (max over ranks); per-stage CUDA events on the "
+                                 "launching streams are in stages_ms"},
             "e2e": {"value": e2e_value, "unit": "constraints/s", "h2d_bytes_per_step": int(z.nbytes + 64),
                     "d2h_bytes_per_step": int(256 + 4 * 2 * 72 * 128 + 2 * 72 * 256), "ms_per_step": 1e3 * t_e2e / args.steps},
             "gpu_launches": int(launches),

@@ -18,7 +18,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, emu_path, out_path):
+def _worker(rank, world, port, emu_path, out_path, curve="bn128"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -26,14 +26,14 @@ def _worker(rank, world, port, emu_path, out_path):
         from zokrates_b200 import backend, distributed, synthetic
         from zokrates_b200._lib import Library
         lib = Library(emu_path)
-        r1cs, z = synthetic.make("bn128", 60, seed=3)
-        ctx0 = backend.context("bn128", 0, lib)
+        r1cs, z = synthetic.make(curve, 60, seed=3)
+        ctx0 = backend.context(curve, 0, lib)
         h = ctx0.r1cs_load(r1cs.num_constraints, r1cs.num_instance, r1cs.num_witness, r1cs.matrices())
         pk = ctx0.setup(h, [3, 5, 7, 11, 13, 17, 19])
-        sess = backend.ProverSession("bn128", r1cs, pk, 0, rank, world, lib=lib)
+        sess = backend.ProverSession(curve, r1cs, pk, 0, rank, world, lib=lib)
         proof = distributed.prove_sharded(sess, z, 111, 222)
         if rank == 0:
-            single = backend.ProverSession("bn128", r1cs, pk, 0, 0, 1, lib=lib).prove_raw(z, 111, 222)
+            single = backend.ProverSession(curve, r1cs, pk, 0, 0, 1, lib=lib).prove_raw(z, 111, 222)
             np.save(out_path, np.array([proof == single, len(proof)]))
         else:
             assert proof is None
@@ -86,6 +86,13 @@ def _worker_chains(rank, world, port, emu_path, out_path):
         np.save(out_path + f".{rank}.npy", np.array([ok]))
     finally:
         dist.destroy_process_group()
+
+
+def test_sharded_prove_gloo_bls12_381(emu_lib, tmp_path):
+    out = str(tmp_path / "res.npy")
+    mp.spawn(_worker, args=(3, _free_port(), emu_lib.path, out, "bls12_381"), nprocs=3, join=True)
+    ok, n = np.load(out)
+    assert ok == 1 and n == 384
 
 
 @pytest.mark.parametrize("world", [3, 4])
