@@ -189,6 +189,7 @@ def test_generate_proof_vs_oracle(cc, shape, gpu_lib):
     assert proof.to_tagged_json() == ark.tagged_proof_json(c, exp, oprog.public_inputs_values(ow))
     if ncons <= 13:
         assert ark.verify(c, ark.pk_deserialize(c, kp.pk), oprog.public_inputs_values(ow), exp)
+        assert backend.B200.verify(kp.vk, proof)        # the product's own host verifier (Backend::verify)
 
 
 @pytest.mark.parametrize("dist", ["uniform", "bits"])

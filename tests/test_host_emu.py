@@ -119,6 +119,7 @@ def test_prove_through_backend_mirror(cc, shape, emu_lib):
     assert proof.to_tagged_json() == ark.tagged_proof_json(c, oproof, oinputs)
     if ncons <= 5:
         assert ark.verify(c, ark.pk_deserialize(c, kp.pk), oinputs, oproof)
+        assert backend.B200.verify(kp.vk, proof)        # the product's own host verifier (Backend::verify)
 
 
 def test_sharded_partials_equal_single(cc):
