@@ -142,9 +142,18 @@ def test_file_level_pipeline_on_the_emulated_engine(tmp_path, emu_lib, monkeypat
         zkb_compute_witness.main(["-i", str(tmp_path / "out"), "-o", str(tmp_path / "w2"), "-a", "3", "10"])
     with pytest.raises(SystemExit, match="Could not parse argument"):
         zkb_compute_witness.main(["-i", str(tmp_path / "out"), "-o", str(tmp_path / "w2"), "-a", "x"])
-    td = [11, 22, 33, 44, 55555, 3, 7]
+    from tools import zkb_setup, zkb_verify
+    rc = zkb_setup.main(["-i", str(tmp_path / "out"), "-p", str(tmp_path / "proving.key"), "-v", str(tmp_path / "verification.key"),
+                         "-e", "ceremony"])
+    assert rc == 0
+    from zokrates_b200 import rng as prng2, proof as pproof2
+    c_prod = backend._curve("bn128")
+    r_setup = prng2.get_rng_from_entropy("ceremony")
+    td = [prng2.fr_rand(c_prod, r_setup) for _ in range(7)]       # alpha, beta, gamma, delta, tau and the two generator scalars
     kp = backend.B200.setup(prog, td)
-    (tmp_path / "proving.key").write_bytes(kp.pk)
+    assert (tmp_path / "proving.key").read_bytes() == kp.pk
+    assert (tmp_path / "verification.key").read_text() == kp.vk.to_tagged_json()
+    assert pproof2.VerificationKey.from_json(kp.vk.to_tagged_json()) == kp.vk
     rc = zkb_generate_proof.main(["-i", str(tmp_path / "out"), "-w", str(tmp_path / "witness"), "-p", str(tmp_path / "proving.key"),
                                   "-j", str(tmp_path / "proof.json"), "-e", "pipeline"])
     assert rc == 0
@@ -156,3 +165,15 @@ def test_file_level_pipeline_on_the_emulated_engine(tmp_path, emu_lib, monkeypat
     r, s = ark.fr_rand(c, orng), ark.fr_rand(c, orng)
     exp = ark.trapdoor_expected_proof(c, r1cs_o, ark.Trapdoor(*td), z, r, s)
     assert (tmp_path / "proof.json").read_text() == ark.tagged_proof_json(c, exp, [113569])
+    import contextlib
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        assert zkb_verify.main(["-j", str(tmp_path / "proof.json"), "-v", str(tmp_path / "verification.key")]) == 0
+    assert buf.getvalue().splitlines() == ["Performing verification...", "PASSED"]
+    tampered = json.loads((tmp_path / "proof.json").read_text())
+    tampered["inputs"][0] = "0x" + (113570).to_bytes(32, "big").hex()
+    (tmp_path / "bad.json").write_text(json.dumps(tampered))
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        zkb_verify.main(["-j", str(tmp_path / "bad.json"), "-v", str(tmp_path / "verification.key")])
+    assert buf.getvalue().splitlines()[-1] == "FAILED"

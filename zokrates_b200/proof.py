@@ -111,6 +111,16 @@ class VerificationKey:
                            "gamma_abc": [g.to_json() for g in self.gamma_abc]}, indent=2)
 
 
+    @classmethod
+    def from_json(cls, text: str) -> "VerificationKey":
+        d = json.loads(text)
+        if d.get("scheme", SCHEME_NAME) != SCHEME_NAME:
+            raise ValueError("verification key is not for scheme g16")
+        g2 = lambda v: G2Affine(tuple(v[0]), tuple(v[1]))
+        return cls(G1Affine(*d["alpha"]), g2(d["beta"]), g2(d["gamma"]), g2(d["delta"]), [G1Affine(*g) for g in d["gamma_abc"]],
+                   d.get("curve", "bn128"))
+
+
 @dataclass
 class SetupKeypair:
     vk: VerificationKey
