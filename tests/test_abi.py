@@ -54,3 +54,7 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "libzkoracle" not in src and "zkoracle.c" not in src, f
+    for f in os.listdir(os.path.join(ROOT, "tools")):          # the file-level front doors are product code too
+        if f.startswith("zkb_") and f.endswith(".py"):
+            src = open(os.path.join(ROOT, "tools", f)).read()
+            assert not re.search(r"^\s*(from|import)\s+(oracle|tests)\b", src, flags=re.M), f
