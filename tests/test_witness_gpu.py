@@ -54,6 +54,19 @@ def test_unsatisfied_and_errors_emu(emu_lib):
         witness_gpu.generate_witness(Prog([Parameter.private_(x)], 0, [Directive([], [y], "Xor")]), [1], lib=emu_lib)
 
 
+def test_inputs_to_proof_without_leaving_the_device_emu(emu_lib):
+    """witness_eval leaves z resident, prove_resident consumes it: same proof JSON as interpreter + generate_proof."""
+    import io
+    from zokrates_b200 import backend, rng as prng
+    for name, prog, inputs in _programs():
+        kp = backend.B200.setup(prog, [3, 5, 7, 11, 13, 17, 19], lib=emu_lib)
+        ref = backend.B200.generate_proof(prog, ir.Interpreter().execute(prog, inputs), io.BytesIO(kp.pk),
+                                          prng.get_rng_from_entropy("resident"), lib=emu_lib)
+        got = witness_gpu.prove_from_inputs(prog, inputs, io.BytesIO(kp.pk), prng.get_rng_from_entropy("resident"), lib=emu_lib)
+        assert got.to_tagged_json() == ref.to_tagged_json(), name
+        assert backend.B200.verify(kp.vk, got), name
+
+
 def _synthetic_roundtrip(ctx, n):
     """synthetic circuit: forget every computed variable, let the device recompute them, compare with the generator's z;
     then the satisfaction check accepts z and names the first broken row after one value is changed."""

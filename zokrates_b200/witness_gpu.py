@@ -92,3 +92,50 @@ def generate_witness(prog: Prog, inputs: Sequence[int], ctx=None, lib=None) -> W
     for v, col in cols.items():
         w.insert(v, vals[col])
     return w
+
+
+def prove_from_inputs(prog: Prog, inputs: Sequence[int], proving_key, rng, device: int = 0, lib=None):
+    """Inputs -> proof with the assignment never leaving the device between witness generation and proving:
+    `zkb_witness_eval` leaves z resident, `zkb_groth16_prove_resident` consumes it (the reference runs
+    `compute-witness` and `generate-proof` as two processes with a witness file in between).  Same result as
+    `B200.generate_proof(prog, Interpreter().execute(prog, inputs), proving_key, rng)`; directive-free programs only."""
+    from . import backend
+    from ._lib import ZkbError
+    from .proof import Proof
+    from .rng import fr_rand
+    c = _curve(prog.curve)
+    if len(inputs) != len(prog.arguments):
+        raise ValueError(f"WrongInputCount: expected {len(prog.arguments)}, received {len(inputs)}")
+    if any(isinstance(s, Directive) for s in prog.statements):
+        raise NotImplementedError("solver directives have no device path: use ir.Interpreter + B200.generate_proof")
+    pk_bytes = proving_key.read() if hasattr(proving_key, "read") else bytes(proving_key)
+    r = fr_rand(c, rng)                                      # create_random_proof draws r then s before synthesis
+    s = fr_rand(c, rng)
+    r1cs = synthesize(prog)
+    cols = {v: i for i, v in enumerate(r1cs.instance_vars)}
+    cols.update({v: r1cs.num_instance + i for i, v in enumerate(r1cs.witness_vars)})
+    vals = [0] * r1cs.num_variables
+    vals[0] = 1
+    for p, x in zip(prog.arguments, inputs):
+        vals[cols[p.id]] = int(x) % c.r
+    level_ptr, rows, out_var = levelize(r1cs, [0] + [cols[p.id] for p in prog.arguments])
+    sess = backend.ProverSession(c, r1cs, pk_bytes, device, lib=lib)
+    try:
+        z = fr_array(vals)
+        if len(level_ptr) > 1:
+            try:
+                z = sess.ctx.witness_eval(sess.r1cs_h, z, level_ptr, rows, out_var)
+            except ZkbError as e:
+                if e.code == 5:
+                    raise UnsatisfiedConstraint(str(e))
+                raise
+        else:
+            sess.ctx.set_assignment(sess.r1cs_h, z)
+        raw = sess.ctx.prove_resident(sess.pk_h, sess.r1cs_h, r, s)
+        public = fr_from_array(z[1:r1cs.num_instance]) if r1cs.num_instance > 1 else []   # instance columns ...
+    finally:
+        sess.close()
+    # ... but the proof lists public arguments first and return values after them (ir/mod.rs:278-288)
+    by_var = dict(zip(r1cs.instance_vars[1:], public))
+    ordered = [by_var[p.id] for p in prog.arguments if not p.private] + [by_var[Variable.public(i)] for i in range(prog.return_count)]
+    return Proof.from_raw(c, raw, ordered)
