@@ -321,7 +321,8 @@ def main():
                     "traffic_note": "ncu dram__bytes_read+write of this kernel (profiles/r01_ncu_accum1_final.md): the gathers go to 5 GB of "
                                     "HBM-resident window tables 2^(cw)P, a deliberate bytes-for-multiplications trade (19% fewer mixed additions)",
                     "peak_source": hbm_src, "avg_launch_ms": acc_ms,
-                    "note": "the kernel is integer-multiply bound, not HBM bound (230 MAD/B): see roofline_modmul"}
+                    "note": "the kernel is integer-multiply bound, not HBM bound (230 MAD/B): see roofline_modmul",
+                    "binding_resource": "int32-mad", "frac_of_binding_resource": alg_muls / (acc_ms * 1e-3) / modmul_peak}
         roofline_mm = {"kernel": "k_msm_accum1<Fq> (h_query MSM)", "bound": "int32-mad", "achieved": alg_muls / (acc_ms * 1e-3),
                        "peak": modmul_peak, "unit": "Fq-mul/s", "frac": alg_muls / (acc_ms * 1e-3) / modmul_peak,
                        "imad_wide_peak_per_s": imad_peak, "mads_per_mul": 136,
