@@ -319,7 +319,7 @@ def main():
         roofline = {"kernel": "k_msm_accum1<Fq> (h_query MSM)", "bound": "hbm", "achieved": alg_bytes / (acc_ms * 1e-3) / 1e9,
                     "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / (acc_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic,
                     "traffic_note": "ncu dram__bytes_read+write of this kernel (profiles/r01_ncu_accum1_final.md): the gathers go to 5 GB of "
-                                    "HBM-resident window tables 2^(cw)P, a deliberate bytes-for-multiplications trade (19% fewer mixed additions)",
+                                    "HBM-resident window tables 2^(cw)P, a deliberate bytes-for-multiplications trade (14 instead of 16 mixed additions per scalar, one bucket set)",
                     "peak_source": hbm_src, "avg_launch_ms": acc_ms,
                     "note": "the kernel is integer-multiply bound, not HBM bound (230 MAD/B): see roofline_modmul",
                     "binding_resource": "int32-mad", "frac_of_binding_resource": alg_muls / (acc_ms * 1e-3) / modmul_peak}
