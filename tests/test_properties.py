@@ -86,3 +86,5 @@ def test_levelised_evaluation_equals_the_interpreter(emu_lib, case):
     level_ptr, rows, out_var = witness_gpu.levelize(r1cs, [0] + [cols[p.id] for p in prog.arguments])
     assert level_ptr[-1] == r1cs.num_constraints and sorted(rows.tolist()) == list(range(r1cs.num_constraints))
     assert np.all(np.diff(level_ptr.astype(np.int64)) > 0)             # no empty level
+    fast = witness_gpu.levelize_wavefront(r1cs, [0] + [cols[p.id] for p in prog.arguments])
+    assert fast is not None and all(np.array_equal(x, y) for x, y in zip(fast, (level_ptr, rows, out_var)))

@@ -93,6 +93,21 @@ def test_synthetic_roundtrip_emu(emu_lib):
     _synthetic_roundtrip(Context(0, 0, emu_lib), 300)
 
 
+def test_wavefront_levelizer_matches_the_row_loop():
+    for n, seed in ((300, 11), (3000, 3)):
+        r1, z = synthetic.make("bn128", n, seed=seed)
+        m0 = r1.num_variables - n
+        slow = witness_gpu.levelize(r1, range(m0))
+        fast = witness_gpu.levelize_wavefront(r1, range(m0))
+        assert fast is not None and all(np.array_equal(a, b) for a, b in zip(slow, fast))
+        assert all(np.array_equal(a, b) for a, b in zip(witness_gpu.levels_for(r1, range(m0)), slow))
+    # a row that reads a variable nobody defines: the wavefront gives up, the row loop names the row
+    r1, z = synthetic.make("bn128", 50, seed=1)
+    assert witness_gpu.levelize_wavefront(r1, range(3)) is None
+    with pytest.raises(KeyError):
+        witness_gpu.levelize(r1, range(3))
+
+
 @pytest.mark.gpu
 def test_synthetic_roundtrip_gpu(gpu_lib):
     ctx = Context(0, 0, gpu_lib)
