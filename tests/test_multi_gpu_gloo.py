@@ -101,3 +101,36 @@ def test_shared_witness_map_chains_gloo(world, emu_lib, tmp_path):
     mp.spawn(_worker_chains, args=(world, _free_port(), emu_lib.path, out), nprocs=world, join=True)
     for rank in range(world):
         assert np.load(out + f".{rank}.npy")[0] == 1, f"rank {rank}"
+
+
+def _worker_msm(rank, world, port, emu_path, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import random
+        from oracle import ark
+        from oracle.ff import BN254, g1_group
+        from zokrates_b200 import backend, distributed
+        from zokrates_b200._lib import Library, fr_array
+        lib = Library(emu_path)
+        ctx = backend.context("bn128", 0, lib)
+        rnd = random.Random(9)
+        G1 = g1_group(BN254)
+        pts = [G1.mul(BN254.g1, rnd.randrange(1, BN254.r)) for _ in range(11)]
+        pts[4] = None
+        sc = [rnd.choice([0, 1, BN254.r - 1, rnd.randrange(BN254.r)]) for _ in range(11)]
+        got = distributed.msm_g1_sharded(ctx, b"".join(ark.ser_g1(BN254, p) for p in pts), fr_array(sc))
+        ok = got == ark.ser_g1(BN254, G1.msm_naive(pts, sc))
+        zero = distributed.msm_g1_sharded(ctx, b"".join(ark.ser_g1(BN254, p) for p in pts), fr_array([0] * 11))
+        ok = ok and zero == ark.ser_g1(BN254, None)
+        np.save(out_path + f".{rank}.npy", np.array([ok]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_msm_gloo(emu_lib, tmp_path):
+    out = str(tmp_path / "msm")
+    mp.spawn(_worker_msm, args=(3, _free_port(), emu_lib.path, out), nprocs=3, join=True)
+    for rank in range(3):
+        assert np.load(out + f".{rank}.npy")[0] == 1, f"rank {rank}"

@@ -91,3 +91,39 @@ def prove_sharded(session, z: Optional[np.ndarray], r: int, s: int, finalize_ses
     if rank != dst:
         return None
     return (finalize_session or session).finalize(allp, world, r, s)
+
+
+def msm_g1_sharded(ctx, points: bytes, scalars: np.ndarray, group=None, device=None) -> bytes:
+    """BASELINE config 5 at N > 1: sum_i s_i P_i with the (scalar, point) pairs split by contiguous index range over the ranks
+    (every rank passes the FULL vectors and computes only its slice with `zkb_msm_g1`), the per-rank affine results
+    all-gathered (one point per rank) and added on the host.  Returns the point in ark's uncompressed encoding on every rank."""
+    import torch
+    import torch.distributed as dist
+    from .verify import _pairing
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64)
+    n = scalars.shape[0]
+    curve_name = "bn128" if ctx.curve == 0 else "bls12_381"
+    pr = _pairing(curve_name)
+    nb = 2 * pr.c.fq_bytes
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    mine = np.frombuffer(ctx.msm(1, points[lo * nb:hi * nb], scalars[lo:hi]), dtype=np.uint8).copy()
+    t = torch.from_numpy(mine)
+    if device is not None:
+        t = t.to(device)
+    out = torch.empty(world * nb, dtype=torch.uint8, device=t.device)
+    dist.all_gather_into_tensor(out, t, group=group)
+    raw = out.cpu().numpy().tobytes()
+    acc = None
+    for k in range(world):
+        part = raw[k * nb:(k + 1) * nb]
+        if part[-1] & 0x40:                      # infinity flag
+            continue
+        x = int.from_bytes(part[:nb // 2], "little")
+        y = int.from_bytes(part[nb // 2:], "little")
+        acc = pr.g1_add(acc, (x, y))
+    if acc is None:
+        res = bytearray(nb)
+        res[-1] = 0x40
+        return bytes(res)
+    return acc[0].to_bytes(nb // 2, "little") + acc[1].to_bytes(nb // 2, "little")
