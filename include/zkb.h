@@ -61,8 +61,10 @@ int32_t zkb_curve_sizes(int32_t curve, uint64_t out[4]);
 /* ---- proving key ------------------------------------------------------------------------------
  * pk_bytes: exactly what ark's `ProvingKey::serialize_unchecked` wrote, i.e. the `proving.key`
  * file (zokrates_ark/src/groth16.rs:97-98; read back unchecked at :40-42; layout SURVEY.md A.3).
- * rank/world: this context keeps the [rank/world) index slice of every query vector resident in
- * HBM (world = 1 for single-GPU). */
+ * rank/world: this context keeps rank's share of every query vector resident in HBM (world = 1 for
+ * single-GPU): contiguous index ranges, cut where the WORK is equal (a_query / b_query are sparse — points at
+ * infinity are skipped — and the sparsity is not uniform over the index); every rank derives the same cuts
+ * from the key bytes.  The shares also hold the window tables 2^(c w) P built at load time. */
 int32_t zkb_pk_load(zkb_ctx* ctx, const uint8_t* pk_bytes, size_t len, uint32_t rank, uint32_t world,
                     uint64_t* pk_handle);
 /* out[0]=gamma_abc len (= instance count incl. one), out[1]=a_query len (= variables), out[2]=h_query len,
@@ -99,8 +101,9 @@ int32_t zkb_groth16_prove_resident(zkb_ctx* ctx, uint64_t pk_handle, uint64_t r1
                                    const uint64_t* r, const uint64_t* s, uint8_t* proof_out, size_t proof_cap);
 
 /* Multi-GPU: every rank computes the partial sums of its index slice (opaque blob, host memory,
- * zkb_curve_sizes()[3] bytes); the host gathers the `world` blobs (torch.distributed all_gather over
- * NCCL) and any rank finishes the proof. */
+ * zkb_curve_sizes()[3] bytes: five projective points — their representation depends on the order the sort's
+ * atomics produced, so blobs are not comparable byte for byte, only the finished proofs are); the host gathers
+ * the `world` blobs (torch.distributed all_gather over NCCL) and any rank finishes the proof. */
 int32_t zkb_groth16_prove_partial(zkb_ctx* ctx, uint64_t pk_handle, uint64_t r1cs_handle, const uint64_t* z,
                                   uint8_t* partial_out, size_t partial_cap);
 int32_t zkb_groth16_finalize(zkb_ctx* ctx, uint64_t pk_handle, const uint8_t* partials, uint32_t world,

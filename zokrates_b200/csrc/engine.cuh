@@ -435,7 +435,7 @@ class Engine : public EngineBase {
     DevBuf<Fr> val[3];
     DevBuf<Fr> z_canon, z_mont, a, b, c, h;
     bool has_z = false;
-    bool sparse_z = false;  // most assignment values are tiny (bits): the z MSMs are cheap, prefer the shallow per-window trees
+    bool sparse_z = false;  // most assignment values are tiny (bits): the z MSMs are cheap, prefer the per-window bucket sets (shallower reductions)
     // host copies kept for setup (CSC transposition) — small relative to the device data
     std::vector<uint32_t> h_rowptr[3], h_col[3];
   };
@@ -851,7 +851,7 @@ class Engine : public EngineBase {
 
   // B200-first: the query vectors are fixed per key and HBM is large, so keep 2^(c w) P_i for every window w
   // resident.  All windows of an MSM then share one bucket set: larger windows (fewer mixed additions per
-  // scalar), a 16x smaller bucket tree, and no 2^(c w) Horner at the end.
+  // scalar), half as many buckets in total, and no 2^(c w) Horner at the end.
   template <class F>
   void build_table(DevBuf<Affine<F>>& buf, size_t n, uint32_t c, uint32_t W) {
     DevBuf<Affine<F>> tab(n * W);
@@ -1027,7 +1027,7 @@ class Engine : public EngineBase {
   static_assert(sizeof(HostPartial) == sizeof(Partial), "partial layout");
 
   // sample the assignment: a witness dominated by 0/1 values (hash circuits) makes the z MSMs nearly free, and the
-  // proof time is then set by the reduction tails — the windows mode (16 x 2^15 buckets) has the shallower tree.
+  // proof time is then set by the reduction tails — the windows mode (16 x 2^15 buckets) has the shallower reduction.
   static bool assignment_is_sparse(const uint64_t* z, uint64_t m) {
     const uint64_t step = m > 4096 ? m / 4096 : 1;
     uint64_t small = 0, cnt = 0;

@@ -14,7 +14,7 @@
 //              A bucket wholly inside a chunk is written directly; a bucket cut by a chunk border
 //              is deferred as a partial sum to the next (much smaller) level, which runs the same
 //              segmented reduction on XYZZ partials.
-//   bucket tree + window Horner: sum_j j * B_j per window by an L-ary tree, then 2^(c w) weights.
+//   bucket reduction: sum_j (j+1) * B_j by bit sums (msm_bitsum_body); the last few hundred additions run on the host.
 //
 // One "plan" (digits/sort) is reused for every point vector that shares the scalars: a_query,
 // b_g1_query, b_g2_query and l_query all pair with the same assignment vector.
