@@ -71,6 +71,22 @@ int32_t zkb_pk_load(zkb_ctx* ctx, const uint8_t* pk_bytes, size_t len, uint32_t 
  * out[3]=l_query len */
 int32_t zkb_pk_info(zkb_ctx* ctx, uint64_t pk_handle, uint64_t out[4]);
 int32_t zkb_pk_free(zkb_ctx* ctx, uint64_t pk_handle);
+/* HBM-resident window tables 2^(c w) P of this key share (a deliberate bytes-for-multiplications trade):
+ * out[0] = c of the a/b1/b2/l tables (0: none), out[1] = their W, out[2] = c of the h table, out[3] = its W,
+ * out[4] = table bytes, out[5] = resident key bytes (tables included),
+ * out[6] / out[7] = status of the z / h tables: 1 built, 2 MSM below ZKB_OPT_TABLE_MIN_LOG, 3 did not fit in HBM
+ * (the prover then runs the same MSM with per-window bucket sets: slower, never wrong), 4 disabled, 5 no admissible window. */
+int32_t zkb_pk_table_info(zkb_ctx* ctx, uint64_t pk_handle, uint64_t out[8]);
+
+/* Per-context options (the reference has none; its equivalents are cargo features, zokrates_ark/Cargo.toml:8-18).
+ * Defaults are the product configuration; the tests use them to force every code path. */
+#define ZKB_OPT_TABLES 1        /* 0 never build window tables, 1 build them when they fit (default), 2 build or fail ZKB_E_OOM */
+#define ZKB_OPT_TABLE_MIN_LOG 2 /* smallest MSM (log2 pairs) that gets tables; default 14 */
+#define ZKB_OPT_TABLE_C 3       /* forced window width of the tables, 0 = cost model (default) */
+#define ZKB_OPT_Z_MODE 4        /* assignment MSMs: 0 sample z and choose (default), 1 shared-bucket table mode, 2 per-window buckets */
+#define ZKB_OPT_NTT_TILE_MIN 5  /* transforms of 2^k points and more use the shared-memory tile passes; default 10 */
+#define ZKB_OPT_NTT_MAX_S 6     /* stage bits per tile pass, 1..10; default 10 */
+int32_t zkb_ctx_set_option(zkb_ctx* ctx, int32_t option, int64_t value);
 
 /* ---- R1CS -------------------------------------------------------------------------------------
  * Matrices A, B, C in CSR form with columns in ark-relations order (0 = one, then instance

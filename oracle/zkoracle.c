@@ -681,3 +681,122 @@ EXPORT int zko_groth16_setup(int curve, uint64_t N, uint64_t ni, uint64_t nw, co
   free(pw); free(u); free(abc[0]); free(abc[1]); free(abc[2]); free(lq); free(hq);
   return (uint64_t)(o - pk_out) == total ? 0 : 6;
 }
+
+/* ------------------------------------------------------------------------------------------- trapdoor prediction
+ * Expected Groth16 proof (A, B, C) for a key made by zko_groth16_setup / zkb_groth16_setup from the SAME explicit
+ * trapdoor, computed with Fr arithmetic only plus one scalar multiplication of the generator per proof element —
+ * no NTT, no MSM, no proving key (restates oracle/ark.py::trapdoor_expected_proof; Groth16 [ePrint 2016/260] §3.2 with
+ * ark-groth16 0.3.0's element order):
+ *   u_j   = L_j(tau) = Z(tau)/n * w^j / (tau - w^j)            (closed form, batch inversion; NOT an inverse FFT)
+ *   Az    = sum_j u_j <A_j, z> + sum_{i<ni} u_{N+i} z_i ;  Bz, Cz likewise (without the instance rows)
+ *   a     = alpha + Az + r delta ;  b = beta + Bz + s delta
+ *   l     = [ beta (Az - Az|inst) + alpha (Bz - Bz|inst) + (Cz - Cz|inst) ] / delta     (aux variables only)
+ *   h     = (Az Bz - Cz) / delta                                  ( = h(tau) Z(tau) / delta )
+ *   c     = l + h + s a + r b - r s delta
+ *   proof = (a g1, b g2, c g1),  g1 = g1_k G1, g2 = g2_k G2.
+ * Returns 0, or 3 if tau lies in the evaluation domain. */
+EXPORT int zko_trapdoor_expected(int curve, uint64_t N, uint64_t ni, uint64_t nw, const uint64_t* a_rowptr, const uint32_t* a_col,
+                                 const uint64_t* a_val, const uint64_t* b_rowptr, const uint32_t* b_col, const uint64_t* b_val,
+                                 const uint64_t* c_rowptr, const uint32_t* c_col, const uint64_t* c_val, const uint64_t* trapdoor7,
+                                 const uint64_t* z, const uint64_t* r_s, const uint64_t* s_s, uint8_t* proof_out) {
+  curves_init();
+  const curve_t* c = &CURVES[curve];
+  const fctx* f = &c->fr;
+  const int g1b = 2 * c->fq_bytes, g2b = 4 * c->fq_bytes;
+  const uint64_t m = ni + nw, dom = N + ni; size_t n = 1; int lg = 0;
+  while (n < dom) { n <<= 1; lg++; }
+  fe alpha, beta, delta, tau, rr, ss; uint64_t gk[2][4];
+  read_fr(c, &alpha, trapdoor7); read_fr(c, &beta, trapdoor7 + 4); read_fr(c, &delta, trapdoor7 + 12); read_fr(c, &tau, trapdoor7 + 16);
+  memcpy(gk[0], trapdoor7 + 20, 32); memcpy(gk[1], trapdoor7 + 24, 32);
+  read_fr(c, &rr, r_s); read_fr(c, &ss, s_s);
+  /* Lagrange coefficients at tau, chunked: per chunk w^j by one exponentiation + running product, one inversion (Montgomery's trick) */
+  fe w; domain_omega(c, lg, &w);
+  fe zt = tau; for (int i = 0; i < lg; i++) fe_sqr(f, &zt, &zt);
+  fe_sub(f, &zt, &zt, &f->r1);
+  fe nn, ninv, scale; fe_from_u64(f, &nn, n); fe_inv(f, &ninv, &nn); fe_mul(f, &scale, &zt, &ninv);
+  fe* u = (fe*)malloc(n * sizeof(fe));
+  fe* pre = (fe*)malloc(n * sizeof(fe));
+  const int nt = zko_pool_threads();
+  const size_t chunk = (n + nt - 1) / nt;
+  int bad = 0;
+#pragma omp parallel for schedule(static) num_threads(nt)
+  for (int t = 0; t < nt; t++) {
+    size_t lo = (size_t)t * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    if (lo >= hi) continue;
+    uint64_t e[1] = {lo};
+    fe wj; fe_pow(f, &wj, &w, e, 1);
+    fe run = f->r1;
+    for (size_t j = lo; j < hi; j++) {              /* u[j] = w^j (kept), pre[j] = prod_{k<j} (tau - w^k) */
+      fe d; fe_sub(f, &d, &tau, &wj);
+      if (fe_is_zero(f, &d)) { bad = 1; d = f->r1; }
+      u[j] = wj; pre[j] = run;
+      fe_mul(f, &run, &run, &d);
+      fe_mul(f, &wj, &wj, &w);
+    }
+    fe inv; fe_inv(f, &inv, &run);
+    for (size_t j = hi; j-- > lo;) {
+      fe d, dinv; fe_sub(f, &d, &tau, &u[j]);
+      fe_mul(f, &dinv, &inv, &pre[j]);              /* 1 / (tau - w^j) */
+      fe_mul(f, &inv, &inv, &d);
+      fe_mul(f, &u[j], &u[j], &dinv);
+      fe_mul(f, &u[j], &u[j], &scale);
+    }
+  }
+  free(pre);
+  if (bad) { free(u); return 3; }
+  fe* zm = load_z(c, z, m);
+  const uint64_t* rp[3] = {a_rowptr, b_rowptr, c_rowptr}; const uint32_t* cl[3] = {a_col, b_col, c_col}; const uint64_t* vl[3] = {a_val, b_val, c_val};
+  fe all[3], inst[3];
+  for (int k = 0; k < 3; k++) {
+    fe* pa = (fe*)calloc(nt, sizeof(fe)); fe* pi = (fe*)calloc(nt, sizeof(fe));
+    const size_t rchunk = (N + nt - 1) / nt;
+#pragma omp parallel for schedule(static) num_threads(nt)
+    for (int t = 0; t < nt; t++) {
+      size_t lo = (size_t)t * rchunk, hi = lo + rchunk < N ? lo + rchunk : N;
+      fe sa, si; memset(&sa, 0, sizeof sa); memset(&si, 0, sizeof si);
+      for (size_t row = lo; row < hi; row++) {
+        fe ra, ri; memset(&ra, 0, sizeof ra); memset(&ri, 0, sizeof ri);
+        for (uint64_t e = rp[k][row]; e < rp[k][row + 1]; e++) {
+          fe v, p; read_fr(c, &v, vl[k] + 4 * e);
+          fe_mul(f, &p, &v, &zm[cl[k][e]]);
+          fe_add(f, &ra, &ra, &p);
+          if (cl[k][e] < ni) fe_add(f, &ri, &ri, &p);
+        }
+        fe_mul(f, &ra, &ra, &u[row]); fe_mul(f, &ri, &ri, &u[row]);
+        fe_add(f, &sa, &sa, &ra); fe_add(f, &si, &si, &ri);
+      }
+      pa[t] = sa; pi[t] = si;
+    }
+    memset(&all[k], 0, sizeof(fe)); memset(&inst[k], 0, sizeof(fe));
+    for (int t = 0; t < nt; t++) { fe_add(f, &all[k], &all[k], &pa[t]); fe_add(f, &inst[k], &inst[k], &pi[t]); }
+    free(pa); free(pi);
+  }
+  for (uint64_t i = 0; i < ni; i++) {               /* the extra rows a[N + i] = z_i of the instance variables */
+    fe p; fe_mul(f, &p, &u[N + i], &zm[i]);
+    fe_add(f, &all[0], &all[0], &p); fe_add(f, &inst[0], &inst[0], &p);
+  }
+  free(u); free(zm);
+  fe dinv; fe_inv(f, &dinv, &delta);
+  fe ad, bd, l, h, cd, t1, t2;
+  fe_mul(f, &t1, &rr, &delta); fe_add(f, &ad, &alpha, &all[0]); fe_add(f, &ad, &ad, &t1);
+  fe_mul(f, &t1, &ss, &delta); fe_add(f, &bd, &beta, &all[1]); fe_add(f, &bd, &bd, &t1);
+  fe_sub(f, &t1, &all[0], &inst[0]); fe_mul(f, &l, &beta, &t1);
+  fe_sub(f, &t1, &all[1], &inst[1]); fe_mul(f, &t2, &alpha, &t1); fe_add(f, &l, &l, &t2);
+  fe_sub(f, &t1, &all[2], &inst[2]); fe_add(f, &l, &l, &t1);
+  fe_mul(f, &l, &l, &dinv);
+  fe_mul(f, &h, &all[0], &all[1]); fe_sub(f, &h, &h, &all[2]); fe_mul(f, &h, &h, &dinv);
+  fe_add(f, &cd, &l, &h);
+  fe_mul(f, &t1, &ss, &ad); fe_add(f, &cd, &cd, &t1);
+  fe_mul(f, &t1, &rr, &bd); fe_add(f, &cd, &cd, &t1);
+  fe_mul(f, &t1, &rr, &ss); fe_mul(f, &t1, &t1, &delta); fe_sub(f, &cd, &cd, &t1);
+  fe ac, bc, cc; fe_from_mont(f, &ac, &ad); fe_from_mont(f, &bc, &bd); fe_from_mont(f, &cc, &cd);
+  g1_aff s1; g2_aff s2; std_generators(curve, c, &s1, &s2);
+  g1_jac j1, g1, pa1, pc1; g2_jac j2, g2, pb2;
+  g1_from_affine(&c->fq, &j1, &s1); g2_from_affine(&c->fq, &j2, &s2);
+  g1_mul(&c->fq, &g1, &j1, gk[0], 4); g2_mul(&c->fq, &g2, &j2, gk[1], 4);
+  g1_mul(&c->fq, &pa1, &g1, ac.l, 4); g2_mul(&c->fq, &pb2, &g2, bc.l, 4); g1_mul(&c->fq, &pc1, &g1, cc.l, 4);
+  g1_aff oa, oc; g2_aff ob;
+  g1_to_affine(&c->fq, &oa, &pa1); g2_to_affine(&c->fq, &ob, &pb2); g1_to_affine(&c->fq, &oc, &pc1);
+  g1_write(c, proof_out, &oa); g2_write(c, proof_out + g1b, &ob); g1_write(c, proof_out + g1b + g2b, &oc);
+  return 0;
+}

@@ -86,3 +86,18 @@ class OracleC:
             if rc != 2:
                 raise RuntimeError(f"zko_groth16_setup rc={rc}")
             cap = int(n.value)
+
+    def trapdoor_expected(self, curve, r1cs, trapdoor7, z, r: int, s: int, fq_bytes):
+        """Expected proof bytes from the trapdoor (Fr arithmetic + three generator multiplications; no NTT / MSM / key)."""
+        from zokrates_b200._lib import fr_array
+        td = fr_array(trapdoor7)
+        z = np.ascontiguousarray(z, dtype=np.uint64)
+        ra, sa = fr_array([r]), fr_array([s])
+        out = np.zeros(8 * fq_bytes, dtype=np.uint8)
+        args, keep = self._mats(r1cs)
+        rc = self.dll.zko_trapdoor_expected(curve, C.c_uint64(r1cs.num_constraints), C.c_uint64(r1cs.num_instance),
+                                            C.c_uint64(r1cs.num_witness), *args, C.c_void_p(td.ctypes.data), C.c_void_p(z.ctypes.data),
+                                            C.c_void_p(ra.ctypes.data), C.c_void_p(sa.ctypes.data), C.c_void_p(out.ctypes.data))
+        if rc != 0:
+            raise RuntimeError(f"zko_trapdoor_expected rc={rc}")
+        return out.tobytes()

@@ -213,26 +213,6 @@ def test_prove_vs_c_oracle_mid(cc, oracle_c, dist):
     assert ctx.prove_resident(pkh, h, 111, 222) == proof
 
 
-def test_prove_full_size_sharding_invariance(gpu_lib):
-    """BASELINE config 3 size (2^20 - 2 constraints, BN254): the proof is identical for 1, 2 and 8-way index
-    sharding, for the layered GPU-generated witness, and changes when r changes (blinding is applied)."""
-    ctx = Context(0, 0, gpu_lib)
-    r1, z = synthetic.make_layered(ctx, "bn128", (1 << 20) - 2)
-    h = ctx.r1cs_load(r1.num_constraints, r1.num_instance, r1.num_witness, r1.matrices())
-    pk = ctx.setup(h, [3, 5, 7, 11, 1234567, 17, 19])
-    pkh = ctx.pk_load(pk)
-    p1 = ctx.prove(pkh, h, z, 111, 222)
-    for world in (2, 8):
-        parts = []
-        for rank in range(world):
-            ph = ctx.pk_load(pk, rank, world)
-            parts.append(ctx.prove_partial(ph, h, z))
-            ctx.pk_free(ph)
-        assert ctx.finalize(pkh, np.concatenate(parts), world, 111, 222) == p1
-    assert ctx.prove(pkh, h, z, 112, 222) != p1
-    ctx.close()
-
-
 def test_error_paths(cc):
     cid, c, ctx = cc
     with pytest.raises(ZkbError) as e:

@@ -187,12 +187,14 @@ def test_prove_synthetic_vs_c_oracle(dist, emu_lib, oracle_c):
 
 
 @pytest.mark.parametrize("log_n,max_s", [(10, 10), (11, 10), (12, 10), (13, 10), (10, 5), (12, 6), (13, 5), (14, 7), (15, 5)])
-def test_ntt_tiled_passes(cc, log_n, max_s, monkeypatch):
+def test_ntt_tiled_passes(cc, log_n, max_s):
     """Shared-memory tile passes (ntt_block_body): one pass (2^10), two balanced passes, and — with the per-pass stage
     limit lowered — three passes with interleaved groups, against the python oracle in all four modes; the register-pass
     schedule (tile path switched off) must give the same vectors."""
     cid, c, ctx = cc
-    monkeypatch.setenv("ZKB_NTT_MAXS", str(max_s))
+    from zokrates_b200._lib import OPT_NTT_MAX_S, OPT_NTT_TILE_MIN
+    ctx.set_option(OPT_NTT_MAX_S, max_s)
+    ctx.set_option(OPT_NTT_TILE_MIN, 10)
     rnd = random.Random(1000 + log_n)
     n = 1 << log_n
     x = [rnd.randrange(c.r) for _ in range(n)]
@@ -203,7 +205,9 @@ def test_ntt_tiled_passes(cc, log_n, max_s, monkeypatch):
     assert fr_from_array(got[1]) == d.ifft(x)
     assert fr_from_array(got[2]) == d.coset_fft(x)
     assert fr_from_array(got[3]) == d.coset_ifft(x)
-    monkeypatch.setenv("ZKB_NTT_TILE_MIN", "30")
+    ctx.set_option(OPT_NTT_TILE_MIN, 30)
     legacy = [ctx.ntt(X), ctx.ntt(X, inverse=True), ctx.ntt(X, coset=True), ctx.ntt(X, inverse=True, coset=True)]
+    ctx.set_option(OPT_NTT_TILE_MIN, 10)
+    ctx.set_option(OPT_NTT_MAX_S, 10)
     for a, b in zip(got, legacy):
         assert np.array_equal(a, b)

@@ -202,6 +202,27 @@ class TestGroth16Oracle:
             proof, _ = oracle_c.prove(cid, pkb, R1, fr_array(z), 1234, 5678, c.fq_bytes)
             exp = ark.trapdoor_expected_proof(c, r1cs, td, z, 1234, 5678)
             assert proof == ark.ser_g1(c, exp[0]) + ark.ser_g2(c, exp[1]) + ark.ser_g1(c, exp[2])
+            # the C trapdoor prediction (closed-form Lagrange coefficients) == the python one (same formula, big ints)
+            assert oracle_c.trapdoor_expected(cid, R1, [5, 6, 7, 8, 99, 2, 3], fr_array(z), 1234, 5678, c.fq_bytes) == proof
+
+    def test_c_trapdoor_prediction_mid_size(self, oracle_c):
+        """zko_trapdoor_expected against the python prediction and the C prover on synthetic circuits with linear-combination
+        rows, a public input and (BLS12-381) the 384-bit base field; tau inside the domain is reported, not mis-evaluated."""
+        from zokrates_b200 import synthetic
+        for cid, c in ((0, BN254), (1, BLS12_381)):
+            r1, z = synthetic.make(c.name, 300)
+            td = [3, 5, 7, 11, 1234567, 17, 19]
+            got = oracle_c.trapdoor_expected(cid, r1, td, z, 111, 222, c.fq_bytes)
+            ref, _ = oracle_c.prove(cid, oracle_c.setup(cid, r1, td), r1, z, 111, 222, c.fq_bytes)
+            assert got == ref
+            rows = [[(int(col), v) for col, v in zip(cols[int(rp[i]):int(rp[i + 1])], fr_from_array(vals[int(rp[i]):int(rp[i + 1])]))]
+                    for rp, cols, vals in r1.matrices() for i in range(r1.num_constraints)]
+            N = r1.num_constraints
+            o = ark.R1CS(r1.num_instance, r1.num_witness, rows[:N], rows[N:2 * N], rows[2 * N:])
+            exp = ark.trapdoor_expected_proof(c, o, ark.Trapdoor(*td), fr_from_array(z), 111, 222)
+            assert got == ark.ser_g1(c, exp[0]) + ark.ser_g2(c, exp[1]) + ark.ser_g1(c, exp[2])
+            with pytest.raises(RuntimeError, match="rc=3"):
+                oracle_c.trapdoor_expected(cid, r1, td[:4] + [1] + td[5:], z, 111, 222, c.fq_bytes)   # tau = 1 = w^0
 
 
 def _csr(rows, r):

@@ -26,7 +26,11 @@ SYMBOLS = [
     "zkb_msm_g1", "zkb_msm_g2", "zkb_ntt", "zkb_witness_map", "zkb_field_op", "zkb_groth16_setup",
     "zkb_groth16_setup_size", "zkb_last_timings", "zkb_launch_count", "zkb_peak_probe", "zkb_groth16_prove_begin",
     "zkb_groth16_prove_end", "zkb_groth16_finalize_prepare", "zkb_r1cs_check", "zkb_witness_eval",
+    "zkb_pk_table_info", "zkb_ctx_set_option",
 ]
+
+OPT_TABLES, OPT_TABLE_MIN_LOG, OPT_TABLE_C, OPT_Z_MODE, OPT_NTT_TILE_MIN, OPT_NTT_MAX_S = 1, 2, 3, 4, 5, 6
+TABLE_STATUS = {0: "none", 1: "built", 2: "below-min-size", 3: "no-memory", 4: "disabled", 5: "no-window"}
 
 
 class ZkbError(RuntimeError):
@@ -63,6 +67,8 @@ class Library:
         d.zkb_pk_load.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, _u64p]
         d.zkb_pk_info.argtypes = [C.c_void_p, C.c_uint64, _u64p]
         d.zkb_pk_free.argtypes = [C.c_void_p, C.c_uint64]
+        d.zkb_pk_table_info.argtypes = [C.c_void_p, C.c_uint64, _u64p]
+        d.zkb_ctx_set_option.argtypes = [C.c_void_p, C.c_int32, C.c_int64]
         d.zkb_r1cs_load.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64] + [C.c_void_p] * 9 + [_u64p]
         d.zkb_r1cs_free.argtypes = [C.c_void_p, C.c_uint64]
         d.zkb_r1cs_set_assignment.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
@@ -165,6 +171,16 @@ class Context:
 
     def pk_free(self, h):
         self.lib.check(self.lib.dll.zkb_pk_free(self.h, h))
+
+    def pk_table_info(self, h) -> dict:
+        out = (C.c_uint64 * 8)()
+        self.lib.check(self.lib.dll.zkb_pk_table_info(self.h, h, out))
+        v = [int(x) for x in out]
+        return {"c_z": v[0], "W_z": v[1], "c_h": v[2], "W_h": v[3], "table_bytes": v[4], "resident_bytes": v[5],
+                "z_tables": TABLE_STATUS.get(v[6], v[6]), "h_table": TABLE_STATUS.get(v[7], v[7])}
+
+    def set_option(self, option: int, value: int):
+        self.lib.check(self.lib.dll.zkb_ctx_set_option(self.h, option, value))
 
     def r1cs_load(self, n_constraints, n_instance, n_witness, mats) -> int:
         """mats: three (rowptr uint64[N+1], col uint32[nnz], val uint64[nnz,4]) tuples."""

@@ -137,6 +137,23 @@ int32_t zkb_pk_load(zkb_ctx* ctx, const uint8_t* pk, size_t len, uint32_t rank, 
 int32_t zkb_pk_info(zkb_ctx* ctx, uint64_t h, uint64_t out[4]) {
   return guard(ctx, [&] { if (!out) throw Error(ZKB_E_ARG, "null"); ctx->eng->pk_info(h, out); });
 }
+int32_t zkb_pk_table_info(zkb_ctx* ctx, uint64_t h, uint64_t out[8]) {
+  return guard(ctx, [&] { if (!out) throw Error(ZKB_E_ARG, "null"); ctx->eng->pk_table_info(h, out); });
+}
+int32_t zkb_ctx_set_option(zkb_ctx* ctx, int32_t opt, int64_t value) {
+  return guard(ctx, [&] {
+    Options& o = ctx->eng->opts;
+    switch (opt) {
+      case ZKB_OPT_TABLES: if (value < 0 || value > 2) throw Error(ZKB_E_ARG, "ZKB_OPT_TABLES: 0, 1 or 2"); o.tables = value; break;
+      case ZKB_OPT_TABLE_MIN_LOG: if (value < 0 || value > 40) throw Error(ZKB_E_ARG, "ZKB_OPT_TABLE_MIN_LOG"); o.table_min_log = value; break;
+      case ZKB_OPT_TABLE_C: if (value < 0 || value > 22) throw Error(ZKB_E_ARG, "ZKB_OPT_TABLE_C: 0 or 4..22"); o.table_c = value; break;
+      case ZKB_OPT_Z_MODE: if (value < 0 || value > 2) throw Error(ZKB_E_ARG, "ZKB_OPT_Z_MODE: 0, 1 or 2"); o.z_mode = value; break;
+      case ZKB_OPT_NTT_TILE_MIN: if (value < 0 || value > 64) throw Error(ZKB_E_ARG, "ZKB_OPT_NTT_TILE_MIN"); o.ntt_tile_min = value; break;
+      case ZKB_OPT_NTT_MAX_S: if (value < 1 || value > 10) throw Error(ZKB_E_ARG, "ZKB_OPT_NTT_MAX_S: 1..10"); o.ntt_max_s = value; break;
+      default: throw Error(ZKB_E_ARG, "unknown option");
+    }
+  });
+}
 int32_t zkb_pk_free(zkb_ctx* ctx, uint64_t h) { return guard(ctx, [&] { ctx->eng->pk_free(h); }); }
 
 int32_t zkb_r1cs_load(zkb_ctx* ctx, uint64_t N, uint64_t ni, uint64_t nw, const uint64_t* a_rowptr, const uint32_t* a_col,

@@ -314,18 +314,10 @@ class Engine : public EngineBase {
   }
 
   // Transforms of 2^10 and more points run as shared-memory tile passes (ntt_block_body: 10 stages per HBM round
-  // trip); smaller ones as register passes (3 stages per round trip).  ZKB_NTT_TILE_MIN / ZKB_NTT_MAXS: test knobs.
-  static uint32_t ntt_tile_min() {
-    const char* e = getenv("ZKB_NTT_TILE_MIN");   // read per call: the tests flip it inside one process
-    const uint32_t v = e ? (uint32_t)atoi(e) : NTT_TILE_LOG;
-    return v < NTT_TILE_LOG ? NTT_TILE_LOG : v;
-  }
-  static uint32_t ntt_max_s() {
-    const char* e = getenv("ZKB_NTT_MAXS");
-    const uint32_t v = e ? (uint32_t)atoi(e) : NTT_TILE_LOG;
-    return v < 5 ? 5 : v;
-  }
-  static bool ntt_tiled(uint32_t log_n) { return log_n >= ntt_tile_min(); }
+  // trip); smaller ones as register passes (3 stages per round trip).  ZKB_OPT_NTT_TILE_MIN / ZKB_OPT_NTT_MAX_S: test knobs.
+  uint32_t ntt_tile_min() const { return opts.ntt_tile_min < (int64_t)NTT_TILE_LOG ? NTT_TILE_LOG : (uint32_t)opts.ntt_tile_min; }
+  uint32_t ntt_max_s() const { return opts.ntt_max_s < 5 ? 5u : (uint32_t)opts.ntt_max_s; }
+  bool ntt_tiled(uint32_t log_n) const { return log_n >= ntt_tile_min(); }
 
   // natural -> bit-reversed
   void ntt_dif(Fr* x, const Fr* tw, uint32_t log_n) {
@@ -820,6 +812,8 @@ class Engine : public EngineBase {
     DevBuf<G1A> fixed1;                          // alpha1, beta1, delta1, a_query[0], b_g1_query[0]
     DevBuf<G2A> fixed2;                          // beta2, delta2, b_g2_query[0]
     uint32_t pre_cz = 0, pre_ch = 0;             // != 0: a/b1/b2/l (resp. h) hold W window tables 2^(c w) P (HBM-resident precomputation)
+    int z_status = 0, h_status = 0;              // why the tables were (not) built: TAB_* codes, reported by zkb_pk_table_info
+    size_t table_bytes = 0;
     DevBuf<uint8_t> skip;                        // per assignment index: bit0 = a_query point is infinity, bit1 = b_query point is infinity
     HG1A h_fixed1[5];                            // host copies (Montgomery form) for the serial tail
     HG2A h_fixed2[3];
@@ -861,39 +855,61 @@ class Engine : public EngineBase {
     stream_sync(st_);
     buf = std::move(tab);
   }
+  // Table status codes reported by zkb_pk_table_info (out[6] for the z tables, out[7] for the h table).
+  enum { TAB_BUILT = 1, TAB_TOO_SMALL = 2, TAB_NO_MEMORY = 3, TAB_DISABLED = 4, TAB_NO_WINDOW = 5 };
   void precompute_tables(Pk& p) {
-    const char* env = getenv("ZKB_PRECOMP");
-    if (env && atoi(env) == 0) return;
     const uint64_t cnt = p.hi - p.lo, hcnt = p.hhi - p.hlo;
-    auto plan = [&](uint64_t n, uint32_t& c, uint32_t& W) {
+    p.z_status = p.h_status = TAB_DISABLED;
+    if (opts.tables == 0) return;
+    auto plan = [&](uint64_t n, uint32_t& c, uint32_t& W, int& status) {
       c = 0; W = 0;
-      const char* emin = getenv("ZKB_PRECOMP_MIN");   // test hooks: minimum size / forced window width
-      const char* ec = getenv("ZKB_PRECOMP_C");
-      if (n < (uint64_t)(emin ? atoll(emin) : (1 << 14))) return;   // small MSMs are latency-bound; tables buy nothing
+      if (n < (1ull << opts.table_min_log)) { status = TAB_TOO_SMALL; return; }   // small MSMs are latency-bound; tables buy nothing
       // the search is restricted to W <= 16 (an 8-way shard of 2^20 would otherwise pick c = 15, W = 17 and lose the tables)
-      uint32_t cc = ec ? (uint32_t)atoi(ec) : msm_pick_c_pre(n, C::FR_BITS);
-      if (cc == 0) return;
-      uint32_t ww = (C::FR_BITS + 1 + cc - 1) / cc;
-      if (ww > 16) return;
-      c = cc; W = ww;
+      uint32_t cc = opts.table_c ? (uint32_t)opts.table_c : msm_pick_c_pre(n, C::FR_BITS);
+      uint32_t ww = cc ? (C::FR_BITS + 1 + cc - 1) / cc : 0;
+      if (cc == 0 || ww > 16) { status = TAB_NO_WINDOW; return; }
+      c = cc; W = ww; status = TAB_BUILT;
     };
     uint32_t cz, Wz, ch, Wh;
-    plan(cnt, cz, Wz);
-    plan(hcnt, ch, Wh);
-    size_t need = (size_t)Wz * cnt * (3 * G1B + G2B) + (size_t)Wh * hcnt * G1B;
+    plan(cnt, cz, Wz, p.z_status);
+    plan(hcnt, ch, Wh, p.h_status);
+    // HBM budget: the tables must leave room for the sort plans (digits + 3 sorted views: 16 B per (pair, window)), the bucket
+    // sets and the witness-map vectors of the circuit this key belongs to, plus 1 GiB of slack.
+    const size_t need_z = (size_t)Wz * cnt * (3 * G1B + G2B), need_h = (size_t)Wh * hcnt * G1B;
+    const size_t reserve = (size_t)16 * (cnt * (Wz ? Wz : 17) + hcnt * (Wh ? Wh : 17)) + 6 * (p.hl + 1) * FRB + ((size_t)1 << 30);
 #if !defined(ZKB_EMU)
     size_t free_b = 0, total_b = 0;
     ZKB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    if (need > free_b / 2) return;             // keep room for the sort buffers and other keys
 #else
-    (void)need;
+    size_t free_b = ~(size_t)0 >> 1;
 #endif
-    if (cz) {
+    size_t avail = free_b > reserve ? free_b - reserve : 0;
+    auto fits = [&](size_t need, int& status, const char* what) {
+      if (status != TAB_BUILT) return false;
+      if (need <= avail) { avail -= need; return true; }
+      if (opts.tables == 2)
+        throw Error(ZKB_E_OOM, std::string("window tables for ") + what + " need " + std::to_string(need >> 20) + " MiB, " +
+                                   std::to_string(avail >> 20) + " MiB available (ZKB_OPT_TABLES = 2)");
+      status = TAB_NO_MEMORY;
+      return false;
+    };
+    // the z tables serve four MSMs (one of them G2) and come first
+    if (fits(need_z, p.z_status, "a/b1/b2/l")) {
       build_table<Fq>(p.a, cnt, cz, Wz); build_table<Fq>(p.b1, cnt, cz, Wz); build_table<Fq>(p.l, cnt, cz, Wz);
       build_table<Fq2>(p.b2, cnt, cz, Wz);
       p.pre_cz = cz;
+      p.table_bytes += need_z;
     }
-    if (ch) { build_table<Fq>(p.h, hcnt, ch, Wh); p.pre_ch = ch; }
+    if (fits(need_h, p.h_status, "h")) { build_table<Fq>(p.h, hcnt, ch, Wh); p.pre_ch = ch; p.table_bytes += need_h; }
+  }
+  // out: c_z, W_z, c_h, W_h, table bytes, resident key bytes (tables included), z status, h status
+  void pk_table_info(uint64_t h, uint64_t out[8]) override {
+    Pk& p = get_pk(h);
+    auto Wof = [](uint32_t c) -> uint64_t { return c ? (uint64_t)((C::FR_BITS + 1 + c - 1) / c) : 0; };
+    out[0] = p.pre_cz; out[1] = Wof(p.pre_cz); out[2] = p.pre_ch; out[3] = Wof(p.pre_ch);
+    out[4] = p.table_bytes;
+    out[5] = p.a.bytes() + p.b1.bytes() + p.l.bytes() + p.b2.bytes() + p.h.bytes();
+    out[6] = (uint64_t)p.z_status; out[7] = (uint64_t)p.h_status;
   }
 
   uint64_t pk_load(const uint8_t* pk, size_t len, uint32_t rank, uint32_t world) override {
@@ -1035,6 +1051,8 @@ class Engine : public EngineBase {
     return cnt && small * 2 > cnt;
   }
 
+  bool z_window_mode(const R1cs& r) const { return opts.z_mode == 2 || (opts.z_mode == 0 && r.sparse_z); }
+
   // One proof's device work in two calls so that the host can exchange witness-map chains between them:
   //   begin: upload z, start the chains of `chain_mask` on the witness-map stream, the z plan and the four z-MSMs on the
   //          main stream; if some chains are left to other ranks, wait until this rank's chains are complete
@@ -1073,16 +1091,14 @@ class Engine : public EngineBase {
     // The witness map (3 SpMV, 7 NTT, latency/bandwidth-bound at this size) and the h digit plan go to a second
     // stream and fill the multiply-pipe bubbles of the z-dependent MSMs running on the main stream.
     if (!has_wm_stream_) {
-      // high priority by default: its small kernels slot in between the blocks of the big accumulate kernels
-      const char* e = getenv("ZKB_WM_PRIO");
-      wm_stream_ = (e && atoi(e) == 0) ? stream_create() : stream_create_high_priority();
+      // high priority: its small kernels slot in between the blocks of the big accumulate kernels
+      wm_stream_ = stream_create_high_priority();
       has_wm_stream_ = true;
     }
     // The witness map starts at once on its own stream.  Letting the z plan run alone first (ZKB_WM_EARLY=0) shortens the
     // plan from 2.3 to 0.8 ms but the displaced witness-map work then slows the accumulate kernels by the same amount
     // (measured 21.03 vs 20.97 ms, profiles/r01_tuning_log.md): the proof is work-bound, not schedule-bound.
-    static const int wm_early_env = getenv("ZKB_WM_EARLY") ? atoi(getenv("ZKB_WM_EARLY")) : 1;
-    const bool wm_early = wm_early_env != 0;
+    const bool wm_early = true;
     tm2_.reset(new StageTimer(wm_stream_));
     StageTimer& tm2 = *tm2_;
     auto enqueue_chains = [&]() {
@@ -1094,7 +1110,7 @@ class Engine : public EngineBase {
     };
     if (wm_early) enqueue_chains();
     tm.begin("msm_plan_z");
-    plan_build(plan_z_, r.z_canon.p + 1 + pk.lo, pk.hi - pk.lo, 3, pk.skip.p, r.sparse_z ? 0 : pk.pre_cz);
+    plan_build(plan_z_, r.z_canon.p + 1 + pk.lo, pk.hi - pk.lo, 3, pk.skip.p, z_window_mode(r) ? 0 : pk.pre_cz);
     tm.end();
     if (!wm_early) enqueue_chains();
     msm_exec<Fq2>(plan_z_, pk.b2.p, w_b2, ws_[4], &tm, "accum1_g2_b2", 2, "tail_g2_b2");

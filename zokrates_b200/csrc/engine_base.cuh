@@ -6,8 +6,21 @@
 
 namespace zkb {
 
+// Per-context tuning / test options (zkb_ctx_set_option).  Defaults are the product configuration; nothing on a hot path
+// reads the environment.
+struct Options {
+  int64_t tables = 1;         // ZKB_OPT_TABLES: 0 never build window tables, 1 auto (build when they fit), 2 build or fail with ZKB_E_OOM
+  int64_t table_min_log = 14; // ZKB_OPT_TABLE_MIN_LOG: smallest MSM (log2 pairs) that gets tables
+  int64_t table_c = 0;        // ZKB_OPT_TABLE_C: forced window width (0: cost model)
+  int64_t z_mode = 0;         // ZKB_OPT_Z_MODE: 0 sample the assignment, 1 always the shared-bucket table mode, 2 always per-window buckets
+  int64_t ntt_tile_min = 10;  // ZKB_OPT_NTT_TILE_MIN: transforms of 2^k points and more use the shared-memory tile passes
+  int64_t ntt_max_s = 10;     // ZKB_OPT_NTT_MAX_S: stage bits per tile pass
+};
+
 struct EngineBase {
   virtual ~EngineBase() {}
+  Options opts;
+  virtual void pk_table_info(uint64_t h, uint64_t out[8]) = 0;
   virtual void sizes(uint64_t out[4]) = 0;
   virtual uint64_t pk_load(const uint8_t* pk, size_t len, uint32_t rank, uint32_t world) = 0;
   virtual void pk_info(uint64_t h, uint64_t out[4]) = 0;
