@@ -195,8 +195,9 @@ static void curves_init(void) {
 /* OpenMP team size: never more than the CPUs this process may actually run on (affinity mask and cgroup quota) —
  * an oversubscribed team spends its time in barriers. */
 #include <sched.h>
+static int zko_threads_cached = 0;
 static int zko_pool_threads(void) {
-  static int cached = 0;
+#define cached zko_threads_cached
   if (cached) return cached;
   int n = 1;
 #ifdef _OPENMP
@@ -212,6 +213,7 @@ static int zko_pool_threads(void) {
 #endif
   cached = n;
   return n;
+#undef cached
 }
 static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
@@ -382,9 +384,11 @@ static fe* witness_map(const curve_t* c, const r1cs_t* r, const fe* z, int* log_
 #define EXPORT __attribute__((visibility("default")))
 
 EXPORT int zko_threads(void) { return zko_pool_threads(); }
+/* explicit team size (bench.py passes the usable core count so that a launcher's OMP_NUM_THREADS=1 — torchrun sets it for
+ * every rank — cannot starve the CPU arm) */
 EXPORT void zko_set_threads(int n) {
 #ifdef _OPENMP
-  if (n > 0) omp_set_num_threads(n);
+  if (n > 0) { omp_set_num_threads(n); zko_threads_cached = n; }
 #else
   (void)n;
 #endif
@@ -394,6 +398,7 @@ EXPORT void zko_set_threads(int n) {
 EXPORT int zko_field_op(int curve, int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n) {
   curves_init();
   const fctx* f = field == 0 ? &CURVES[curve].fr : &CURVES[curve].fq;
+#pragma omp parallel for schedule(static)
   for (uint64_t i = 0; i < n; i++) {
     fe x, y, r; memset(&x, 0, sizeof x); memset(&y, 0, sizeof y);
     memcpy(x.l, a + i * f->n, 8 * f->n); if (b) memcpy(y.l, b + i * f->n, 8 * f->n);

@@ -12,6 +12,9 @@ class OracleC:
     def threads(self):
         return self.dll.zko_threads()
 
+    def set_threads(self, n: int):
+        self.dll.zko_set_threads(int(n))
+
     def field_op(self, curve, field, op, a, b):
         a = np.ascontiguousarray(a, dtype=np.uint64)
         out = np.zeros_like(a)
