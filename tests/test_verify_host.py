@@ -58,3 +58,20 @@ def test_agrees_with_the_oracle_pairing():
     oproof = ((f[0], f[1]), ((f[2], f[3]), (f[4], f[5])), (f[6], f[7]))
     assert ark.verify(c, pk, pub, oproof) is True and backend.B200.verify(vk, proof) is True
     assert vk.to_tagged_json().startswith('{\n  "scheme": "g16",\n  "curve": "bn128"')
+
+
+def test_degenerate_g2_point_is_a_failed_verification_not_a_crash(monkeypatch):
+    """a vertical line in the Miller loop (G2 input outside the prime-order subgroup) used to surface as a
+    TypeError; the reference's verify returns false.  R + (-R) raises DegeneratePoint and verify_proof maps it to False."""
+    from zokrates_b200 import verify as V
+    v = json.load(open(GOLD))[0]
+    c, pk, vk, proof, pub = _case(v)
+    pr = V._pairing(v["curve"])
+    q = pr.twist(V._g2(proof.proof.b, c.p))
+    with pytest.raises(V.DegeneratePoint):
+        pr._add(q, (q[0], pr.F.neg(q[1])))
+
+    def degenerate(self, pairs):
+        raise V.DegeneratePoint("forced")
+    monkeypatch.setattr(V._Pairing, "product_is_one", degenerate)
+    assert backend.B200.verify(vk, proof) is False

@@ -108,6 +108,82 @@ def test_wavefront_levelizer_matches_the_row_loop():
         witness_gpu.levelize(r1, range(3))
 
 
+def _with_empty_rows(r1, where, rs):
+    """Copy of `r1` with rows `x * 0 == 0`-style (empty B and C combinations) inserted at the given positions."""
+    from zokrates_b200.r1cs import R1CS
+    N = r1.num_constraints
+    keep = np.ones(N + len(where), dtype=bool)
+    keep[np.asarray(where) + np.arange(len(where))] = False        # positions of the inserted rows in the new system
+    mats = []
+    for k, (rp, col, val) in enumerate(r1.matrices()):
+        lens = np.zeros(N + len(where), dtype=np.uint64)
+        lens[keep] = (rp[1:] - rp[:-1]).astype(np.uint64)
+        col, val = col.copy(), val.copy()
+        if k == 0:                                                 # the inserted rows read an input on the A side only
+            extra_c = np.full(len(where), 1, dtype=np.uint32)
+            extra_v = np.zeros((len(where), 4), dtype=np.uint64); extra_v[:, 0] = 1
+            pos = np.cumsum(lens)[~keep].astype(np.int64) + np.arange(len(where))
+            col = np.insert(col, pos - np.arange(len(where)), extra_c)
+            val = np.insert(val, pos - np.arange(len(where)), extra_v, axis=0)
+            lens[~keep] = 1
+        nrp = np.zeros(N + len(where) + 1, dtype=np.uint64)
+        np.cumsum(lens, out=nrp[1:])
+        mats.append((nrp, col, val))
+    return R1CS(r1.curve, N + len(where), r1.num_instance, r1.num_witness, *mats)
+
+
+def test_wavefront_levelizer_with_empty_combinations():
+    """rows whose B / C combinations are empty — in the middle and TRAILING — must not cut the last operand
+    off the preceding row (np.reduceat on clipped start offsets did); levels equal the row loop's at N > 2048."""
+    rs = np.random.RandomState(5)
+    r1, z = synthetic.make("bn128", 2500, seed=7)
+    m0 = r1.num_variables - 2500
+    for where in ([2500], [2500, 2500, 2500], [0, 17, 1200, 2500], sorted(rs.randint(0, 2501, size=40).tolist())):
+        r2 = _with_empty_rows(r1, where, rs)
+        slow = witness_gpu.levelize(r2, range(m0))
+        fast = witness_gpu.levelize_wavefront(r2, range(m0))
+        assert fast is not None and all(np.array_equal(a, b) for a, b in zip(slow, fast)), where
+    # the advisor's shape: u = x * (x + deep) as the last real row, then `x * 0 == 0` rows (empty B and C)
+    from zokrates_b200.r1cs import R1CS
+    r1, z = synthetic.make("bn128", 2100, seed=3)
+    m = r1.num_variables
+    one = np.array([[1, 0, 0, 0]], dtype=np.uint64)
+    (ap, ac, av), (bp, bc, bv), (cp, cc, cv) = r1.matrices()
+    deep = m - 1                                                   # the variable the last synthetic row assigned
+    A = (np.concatenate([ap, [ap[-1] + 1, ap[-1] + 2, ap[-1] + 3]]).astype(np.uint64), np.concatenate([ac, [1, 1, 1]]).astype(np.uint32),
+         np.concatenate([av, one, one, one]))
+    B = (np.concatenate([bp, [bp[-1] + 2, bp[-1] + 2, bp[-1] + 2]]).astype(np.uint64), np.concatenate([bc, [1, deep]]).astype(np.uint32),
+         np.concatenate([bv, one, one]))
+    Cm = (np.concatenate([cp, [cp[-1] + 1, cp[-1] + 1, cp[-1] + 1]]).astype(np.uint64), np.concatenate([cc, [m]]).astype(np.uint32),
+          np.concatenate([cv, one]))
+    r2 = R1CS(r1.curve, 2103, r1.num_instance, r1.num_witness + 1, A, B, Cm)
+    slow = witness_gpu.levelize(r2, range(m - 2100))
+    fast = witness_gpu.levelize_wavefront(r2, range(m - 2100))
+    assert fast is not None and all(np.array_equal(a, b) for a, b in zip(slow, fast))
+
+
+def test_wavefront_levelizer_rejects_read_before_write():
+    """a row that reads a variable assigned by a LATER row is an error in the reference interpreter
+    (lookup of a missing value); the wavefront must not quietly reorder it."""
+    from zokrates_b200.r1cs import R1CS
+    r1, z = synthetic.make("bn128", 2200, seed=9)
+    m0 = r1.num_variables - 2200
+    mats = [list(m) for m in r1.matrices()]
+    # swap rows 100 and 2100 in all three matrices: row 100 now reads variables defined ~2000 rows later
+    perm = np.arange(2200); perm[100], perm[2100] = 2100, 100
+    new = []
+    for rp, col, val in mats:
+        lens = (rp[1:] - rp[:-1]).astype(np.int64)
+        starts = rp[:-1].astype(np.int64)
+        idx = np.concatenate([np.arange(starts[r], starts[r] + lens[r]) for r in perm])
+        nrp = np.zeros(2201, dtype=np.uint64); np.cumsum(lens[perm], out=nrp[1:])
+        new.append((nrp, col[idx], val[idx]))
+    r2 = R1CS(r1.curve, 2200, r1.num_instance, r1.num_witness, *new)
+    assert witness_gpu.levelize_wavefront(r2, range(m0)) is None
+    with pytest.raises(KeyError):
+        witness_gpu.levels_for(r2, range(m0))
+
+
 @pytest.mark.gpu
 def test_synthetic_roundtrip_gpu(gpu_lib):
     ctx = Context(0, 0, gpu_lib)

@@ -37,7 +37,10 @@ def main(argv=None) -> int:
     except (ValueError, KeyError, TypeError) as why:
         raise SystemExit(f"Could not deserialize proof: {why}")
     print("Performing verification...")
-    ok = backend.B200.verify(vk, proof)
+    try:
+        ok = backend.B200.verify(vk, proof)
+    except ValueError as why:                         # malformed key / proof (the reference panics with the same reasons)
+        raise SystemExit(f"Could not verify: {why}")
     print("PASSED" if ok else "FAILED")
     return 0
 

@@ -141,6 +141,10 @@ class Context:
     def __init__(self, curve: int, device: int = 0, lib: Library | None = None):
         self.lib = lib or default_library()
         self.curve = curve
+        # every C-ABI call is serialised per context inside the library; multi-call sequences on shared per-context state
+        # (prove_begin .. prove_end, finalize_prepare .. finalize) take this lock on top
+        import threading
+        self.lock = threading.RLock()
         h = C.c_void_p()
         self.lib.check(self.lib.dll.zkb_ctx_create(curve, device, C.byref(h)))
         self.h = h

@@ -53,12 +53,16 @@ class ProverSession:
         self.ctx = context(self.curve, device, lib)
         self.r1cs = r1cs
         self.rank, self.world = rank, world
-        self.r1cs_h = self.ctx.r1cs_load(r1cs.num_constraints, r1cs.num_instance, r1cs.num_witness, r1cs.matrices())
-        self.pk_h = self.ctx.pk_load(pk_bytes, rank, world)
-        ni, m, hl, ll = self.ctx.pk_info(self.pk_h)
-        if ni != r1cs.num_instance or m != r1cs.num_variables or hl + 1 != r1cs.domain_size:
-            self.close()
-            raise ValueError("proving key does not belong to this program")
+        self.pk_h = self.r1cs_h = None
+        try:
+            self.r1cs_h = self.ctx.r1cs_load(r1cs.num_constraints, r1cs.num_instance, r1cs.num_witness, r1cs.matrices())
+            self.pk_h = self.ctx.pk_load(pk_bytes, rank, world)
+            ni, m, hl, ll = self.ctx.pk_info(self.pk_h)
+            if ni != r1cs.num_instance or m != r1cs.num_variables or hl + 1 != r1cs.domain_size:
+                raise ValueError("proving key does not belong to this program")
+        except BaseException:
+            self.close()          # a failed load must not leave the matrices / key shard resident in the shared context
+            raise
 
     def prove_raw(self, z: np.ndarray, r: int, s: int) -> bytes:
         return self.ctx.prove(self.pk_h, self.r1cs_h, z, r, s)

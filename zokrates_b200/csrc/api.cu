@@ -1,5 +1,6 @@
 // C ABI of libzkb200.so (include/zkb.h).  No exception or CUDA type crosses this boundary.
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "zkb.h"
@@ -18,6 +19,10 @@ struct zkb_ctx {
   Stream st;
   std::unique_ptr<EngineBase> eng;
   uint64_t launches0 = 0;
+  // The reference's static `Backend::generate_proof` is thread-safe; here the engine keeps per-context scratch (sort plans,
+  // bucket sets, timers), so every entry point holds this lock for its whole duration: concurrent callers on one context
+  // are serialised, never interleaved.  (begin/end pairs are additionally guarded by the caller, see _lib.Context.lock.)
+  std::recursive_mutex mu;
 };
 
 static thread_local std::string g_err;
@@ -26,6 +31,7 @@ template <class Fn>
 static int32_t guard(zkb_ctx* ctx, Fn fn) {
   try {
     if (!ctx || !ctx->eng) throw Error(ZKB_E_ARG, "null context");
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
 #if !defined(ZKB_EMU)
     ZKB_CUDA(cudaSetDevice(ctx->device));
 #endif
@@ -290,6 +296,7 @@ int32_t zkb_groth16_setup(zkb_ctx* ctx, uint64_t r1cs, const uint64_t* trapdoor7
 
 int32_t zkb_last_timings(zkb_ctx* ctx, double* ms_out, const char** names_out, int32_t cap) {
   if (!ctx || !ctx->eng) return 0;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   int32_t k = 0;
   for (auto& e : ctx->eng->timings) {
     if (k >= cap) break;

@@ -64,14 +64,15 @@ def prove_partial_shared_wm(ctx, pk_h, r1cs_h, z: Optional[np.ndarray], group=No
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     mask = wm_chain_mask(rank, world)
-    ptrs, nbytes = ctx.prove_begin(pk_h, r1cs_h, z, mask)
-    if mask != 7:
-        for k in range(3):
-            dist.broadcast(chain_tensor(ptrs[k], nbytes, device), src=dist.get_global_rank(group, k % world) if group else k % world,
-                           group=group)
-        if device is not None and str(device) != "cpu":
-            torch.cuda.current_stream(device).synchronize()      # the chains must be in memory before prove_end reads them
-    return ctx.prove_end(pk_h, r1cs_h)
+    with ctx.lock:                                               # one open proof per context: begin .. end is one critical section
+        ptrs, nbytes = ctx.prove_begin(pk_h, r1cs_h, z, mask)
+        if mask != 7:
+            for k in range(3):
+                dist.broadcast(chain_tensor(ptrs[k], nbytes, device), src=dist.get_global_rank(group, k % world) if group else k % world,
+                               group=group)
+            if device is not None and str(device) != "cpu":
+                torch.cuda.current_stream(device).synchronize()  # the chains must be in memory before prove_end reads them
+        return ctx.prove_end(pk_h, r1cs_h)
 
 
 def prove_sharded(session, z: Optional[np.ndarray], r: int, s: int, finalize_session=None, dst: int = 0, group=None,

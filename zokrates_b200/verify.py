@@ -160,7 +160,10 @@ class _Pairing:
         if x1 == x2:
             if y1 == y2:
                 return self._dbl(R)
-            return None, None                      # vertical line, result is infinity (does not occur for valid input)
+            # vertical line: R + Q is the point at infinity.  Cannot happen for points of the prime-order subgroup; an
+            # on-curve point of small order / outside the subgroup can get here (no subgroup check is made, as in the
+            # reference) — such a proof is simply not valid
+            raise DegeneratePoint("Miller loop reached the point at infinity (G2 point outside the prime-order subgroup)")
         m = F.mul(F.sub(y2, y1), F.inv(F.sub(x2, x1)))
         nx = F.sub(F.sub(F.mul(m, m), x1), x2)
         return m, (nx, F.sub(F.mul(m, F.sub(x1, nx)), y1))
@@ -255,6 +258,10 @@ def _g2(pt: G2Affine, p: int):
     return None if not any(v) else ((v[0], v[1]), (v[2], v[3]))
 
 
+class DegeneratePoint(ValueError):
+    """A G2 input drove the Miller loop into the point at infinity: not a point of the prime-order subgroup."""
+
+
 def verify_proof(vk: VerificationKey, proof: Proof) -> bool:
     """True iff the proof satisfies the Groth16 equation under `vk` for its public inputs.  Malformed input raises, as
     the reference panics (`verify_proof(..).unwrap()`, zokrates_ark/src/groth16.rs:85): wrong number of public inputs,
@@ -283,4 +290,7 @@ def verify_proof(vk: VerificationKey, proof: Proof) -> bool:
     for x, g in zip(inputs, abc[1:]):
         acc = pr.g1_add(acc, pr.g1_mul(g, x))
     negA = None if A is None else (A[0], (-A[1]) % c.p)
-    return pr.product_is_one([(negA, B), (alpha, beta), (acc, gamma), (C, delta)])
+    try:
+        return pr.product_is_one([(negA, B), (alpha, beta), (acc, gamma), (C, delta)])
+    except DegeneratePoint:
+        return False                                  # the reference's verify returns false here, it does not crash

@@ -83,18 +83,37 @@ def levelize_wavefront(r1cs: R1CS, defined_cols: Iterable[int], max_levels: int 
         winners = rows_c[first_idx]
         out_var[winners] = first_c[winners].astype(np.uint32)
     assigns = out_var != CHECK
-    # an assigning row must come before every row that reads its variable; the sequential rule guarantees it for valid
-    # programs — verified below through the level recurrence (a reader scheduled before its writer never becomes ready)
+    # An assigning row must come BEFORE (in statement order) every row that reads its variable: the sequential interpreter
+    # fails on a read of a variable that has no value yet (zokrates_interpreter/src/lib.rs:366-378 unwraps the lookup).  The
+    # level recurrence alone would simply schedule such a reader after its writer, so check the order explicitly and leave
+    # invalid programs to `levelize`, which raises like the reference.
+    writer_row = np.full(m, -1, dtype=np.int64)          # -1: defined before the first statement (inputs, one)
+    undefined = level < 0
+    writer_row[undefined] = N                            # never written: any read is an error
+    writer_row[out_var[assigns].astype(np.int64)] = np.flatnonzero(assigns)
+    for ptr, cols, skip_own in ((ap, ac, False), (bp, bc, False), (cp, cc, True)):
+        if not len(cols):
+            continue
+        reader = np.repeat(np.arange(N, dtype=np.int64), ptr[1:] - ptr[:-1])
+        bad = writer_row[cols] >= reader
+        if skip_own:                                     # the assigned variable itself sits on the linear side of its writer
+            bad &= ~(assigns[reader] & (out_var[reader].astype(np.int64) == cols))
+        if bad.any():
+            return None
 
     def seg_max(ptr, cols):
         out = np.zeros(N, dtype=np.int64)
         lens = ptr[1:] - ptr[:-1]
         nz = lens > 0
-        if len(cols):
+        if len(cols) and nz.any():
+            # reduceat over the NON-EMPTY rows only: their start offsets are strictly increasing and < len(cols), so each
+            # segment is exactly one row (a clipped start index for a trailing empty row would cut the last term off the
+            # preceding row)
             vals = level[cols]
-            red = np.maximum.reduceat(vals, np.minimum(ptr[:-1], len(cols) - 1))
-            mn = np.minimum.reduceat(vals, np.minimum(ptr[:-1], len(cols) - 1))
-            out[nz] = np.where(mn[nz] < 0, -1, red[nz])
+            idx = ptr[:-1][nz]
+            red = np.maximum.reduceat(vals, idx)
+            mn = np.minimum.reduceat(vals, idx)
+            out[nz] = np.where(mn < 0, -1, red)
         return out                                  # -1: some operand has no level yet; 0 for empty combinations
 
     row_level = np.full(N, -1, dtype=np.int64)
