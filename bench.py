@@ -105,19 +105,14 @@ class ClockSampler:
                 "power_w_max": max((r[3] for r in inside), default=None)}
 
 
-def usable_cores():
-    try:
-        return len(os.sched_getaffinity(0))
-    except AttributeError:
-        return os.cpu_count() or 1
-
-
 def load_oracle():
     """CPU checker / baseline (oracle/libzkoracle.so).  Only the cpu_baseline leg and --impl reference use it."""
     import __graft_entry__ as g
     from tests.oracle_c import OracleC
     oc = OracleC(g.build_oracle())
-    oc.set_threads(usable_cores())          # explicit: a launcher's OMP_NUM_THREADS=1 must not starve the CPU arm
+    # team size = min(online CPUs, affinity mask, cgroup CPU quota) decided inside the library (zko_pool_threads) and NOT from
+    # OMP_NUM_THREADS: torchrun exports OMP_NUM_THREADS=1 to every rank, which starved this arm in round 1
+    os.environ.pop("OMP_NUM_THREADS", None)
     return oc
 
 
@@ -202,6 +197,8 @@ def main():
     ap.add_argument("--curve", default="bn128", choices=["bn128", "bls12_381"])
     ap.add_argument("--witness", default="uniform", choices=["uniform", "bits"])
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--table-c", type=int, default=0, help="force the window width of the HBM window tables (0: cost model)")
+    ap.add_argument("--pipeline", type=int, default=2, choices=[1, 2], help="proofs in flight per GPU (2: submit i+1 before collecting i)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)          # timing rule: at least three warm-up steps, in both arms
     if args.impl == "reference":
@@ -238,6 +235,9 @@ def main():
     r1cs_h = ctx.r1cs_load(r1cs.num_constraints, r1cs.num_instance, r1cs.num_witness, r1cs.matrices())
     pk = ctx.setup(r1cs_h, TRAPDOOR)
     setup_ms = ctx.timings()
+    if args.table_c:
+        from zokrates_b200._lib import OPT_TABLE_C
+        ctx.set_option(OPT_TABLE_C, args.table_c)
     pk_h = ctx.pk_load(pk, rank, world)
     pk_bytes = len(pk)
     table_info = ctx.pk_table_info(pk_h)
@@ -250,44 +250,51 @@ def main():
     prep_s = time.perf_counter() - t_prep
     r_s = R_S
 
-    def gather_and_finish(partial):
-        """5 partial sums per rank -> all ranks (NCCL all_gather of a few hundred bytes) -> rank 0 finishes."""
-        if world == 1:
-            return ctx.finalize(pk_h, partial, 1, *r_s)
-        from zokrates_b200.distributed import gather_partials
-        allp = gather_partials(partial, device=torch.device("cuda", local))
-        return ctx.finalize(pk_h, allp, world, *r_s) if rank == 0 else None
-
+    dev = torch.device("cuda", local)
     last_stage = {}
 
     # three or more ranks: the witness map's three chains are computed once each and broadcast over NVLink
-    # (zkb_groth16_prove_begin / _end, zokrates_b200/distributed.py); ZKB_WM_SHARE=0 keeps it replicated
+    # (zkb_groth16_prove_begin_async / _end_async, zokrates_b200/distributed.py); ZKB_WM_SHARE=0 keeps it replicated
     share_wm = share_wm_for(world)
 
-    def partial_step(z_arg):
-        if rank == 0:
-            ctx.finalize_prepare(pk_h, *r_s)           # r*delta1 ... s*delta2 on host threads underneath the kernels
+    # Pipelined proving (include/zkb.h: zkb_groth16_prove_submit / _collect): the whole device work of proof i + 1 is enqueued
+    # BEFORE the host collects proof i, so the GPU never idles while the host finishes a proof (last additions of each MSM,
+    # final combination, the all_gather of the partial sums).  Every one of the K proofs is submitted and collected inside
+    # the timed region.  --pipeline 1 proves strictly one at a time (the latency figure).
+    def submit(z_arg):
+        if world == 1:
+            return ctx.prove_submit(pk_h, r1cs_h, z_arg, *r_s)
         if share_wm:
-            from zokrates_b200.distributed import prove_partial_shared_wm
-            partial = prove_partial_shared_wm(ctx, pk_h, r1cs_h, z_arg, device=torch.device("cuda", local))
-        else:
-            partial = ctx.prove_partial(pk_h, r1cs_h, z_arg)
+            from zokrates_b200.distributed import submit_shared_wm
+            return submit_shared_wm(ctx, pk_h, r1cs_h, z_arg, device=dev)
+        return ctx.prove_submit(pk_h, r1cs_h, z_arg)
+
+    def collect(ticket):
+        if world == 1:
+            out = ctx.prove_collect(ticket)
+            last_stage.update(ctx.timings())
+            return out
+        from zokrates_b200.distributed import gather_partials
+        if rank == 0:
+            ctx.finalize_prepare(pk_h, *r_s)           # r*delta1 ... s*delta2 on host threads underneath the gather
+        partial = ctx.prove_collect_partial(ticket)
         last_stage.update(ctx.timings())
-        return gather_and_finish(partial)
+        allp = gather_partials(partial, device=dev)    # 5 partial sums per rank -> all ranks (NCCL all_gather, < 1 kB each)
+        return ctx.finalize(pk_h, allp, world, *r_s) if rank == 0 else None
 
-    def step_resident():
-        if world == 1:
-            out = ctx.prove_resident(pk_h, r1cs_h, *r_s)
-            last_stage.update(ctx.timings())
-            return out
-        return partial_step(None)
-
-    def step_e2e():
-        if world == 1:
-            out = ctx.prove(pk_h, r1cs_h, z_host, *r_s)
-            last_stage.update(ctx.timings())
-            return out
-        return partial_step(z_host)
+    def run_steps(z_arg, steps, on_proof):
+        depth = max(1, min(args.pipeline, 2))
+        pending = []
+        proof = None
+        for _ in range(steps):
+            pending.append(submit(z_arg))
+            if len(pending) >= depth:
+                proof = collect(pending.pop(0))
+                on_proof()
+        while pending:
+            proof = collect(pending.pop(0))
+            on_proof()
+        return proof
 
     def barrier():
         torch.cuda.synchronize()
@@ -295,20 +302,20 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(step_fn, steps):
-        """K steps bracketed by barrier + synchronize; device time via CUDA events on the current stream (each
-        step ends with a stream sync inside the library, so the event pair brackets all device work), max over ranks."""
+    def timed(z_arg, steps):
+        """K proofs bracketed by barrier + synchronize; CUDA events on the current stream bracket the same region (every proof
+        is collected — its device work complete — before the closing event), wall clock and device clock agree; max over ranks."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches0 = ctx.launch_count()
-        t0 = time.perf_counter()
-        e0.record()
         stage = {}
-        proof = None
-        for _ in range(steps):
-            proof = step_fn()
+
+        def on_proof():
             for k, v in last_stage.items():
                 stage[k] = stage.get(k, 0.0) + v
+        t0 = time.perf_counter()
+        e0.record()
+        proof = run_steps(z_arg, steps, on_proof)
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -323,19 +330,28 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(args.warmup):
-        step_resident()
+    run_steps(None, args.warmup, lambda: None)
     tw0 = time.perf_counter()
-    t_res, stage_res, launches, proof = timed(step_resident, args.steps)
+    t_res, stage_res, launches, proof = timed(None, args.steps)
     sampler.mark(tw0, time.perf_counter())
-    for _ in range(2):
-        step_e2e()
+    run_steps(z_host, 2, lambda: None)
     tw0 = time.perf_counter()
-    t_e2e, stage_e2e, _, proof2 = timed(step_e2e, args.steps)
+    t_e2e, stage_e2e, _, proof2 = timed(z_host, args.steps)
     sampler.mark(tw0, time.perf_counter())
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0 and proof != proof2:
         raise SystemExit("resident and e2e proofs differ")
+    # latency of ONE proof with nothing else in flight (what --pipeline 1 would time), after the throughput runs
+    lat = []
+    saved_depth = args.pipeline
+    args.pipeline = 1
+    for _ in range(5):
+        barrier()
+        t0 = time.perf_counter()
+        run_steps(z_host, 1, lambda: None)
+        lat.append(time.perf_counter() - t0)
+    args.pipeline = saved_depth
+    latency_ms = 1e3 * sorted(lat)[len(lat) // 2]
 
     value = n_cons * args.steps / t_res
     e2e_value = n_cons * args.steps / t_e2e
@@ -428,12 +444,14 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "u256-montgomery" if cid == 0 else "u384-montgomery", "data": "synthetic",
             "config": bench_config(args, world, r1cs.num_variables),
             "tables": table_info,
-            "timing": "K proofs bracketed by barrier + synchronize; every proof ends in a stream synchronize inside the library, so "
-                      "the host clock equals the device time of the critical path (max over ranks); per-stage CUDA events on the "
-                      "launching streams are in stages_ms",
+            "timing": "K proofs submitted AND collected between barrier + synchronize (two in flight: proof i+1's device work is enqueued "
+                      "before the host part of proof i runs); wall clock = device clock of the region, max over ranks; per-stage CUDA "
+                      "events on the launching streams are in stages_ms; latency_ms_one_proof_e2e is one proof alone",
             "e2e": {"value": e2e_value, "unit": "constraints/s", "h2d_bytes_per_step": int(z.nbytes + 64),
                     "d2h_bytes_per_step": int(256 + 4 * 2 * 72 * 128 + 2 * 72 * 256), "ms_per_step": 1e3 * t_e2e / args.steps},
             "gpu_launches": int(launches),
+            "pipeline_depth": args.pipeline,
+            "latency_ms_one_proof_e2e": latency_ms,
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

@@ -145,6 +145,22 @@ int32_t zkb_groth16_prove_begin(zkb_ctx* ctx, uint64_t pk_handle, uint64_t r1cs_
 int32_t zkb_groth16_prove_end(zkb_ctx* ctx, uint64_t pk_handle, uint64_t r1cs_handle, uint8_t* partial_out,
                               size_t partial_cap);
 
+/* Pipelined proving: TWO proofs may be in flight per context.  `submit` enqueues a proof's whole device work and returns
+ * without synchronising; `collect` waits for it and runs the host tail.  While the host finishes proof i (the last additions
+ * of each MSM, the final combination, a multi-GPU gather) the GPU already runs proof i + 1, whose digit plans and
+ * accumulate kernels overlap the latency-bound reduction tails of proof i — the reference proves strictly one at a time
+ * (zokrates_cli/src/ops/generate_proof.rs:152-202 is one process per proof).
+ *   submit: z may be NULL (resident assignment); r, s both NULL (partial only) or both given (finished proof).
+ *   collect / collect_partial: in any order, each ticket once.  A third submit before a collect fails with ZKB_E_ARG.
+ *   begin_async / end_async: the chain-exchange form (see above) without the synchronising collect. */
+int32_t zkb_groth16_prove_submit(zkb_ctx* ctx, uint64_t pk_handle, uint64_t r1cs_handle, const uint64_t* z,
+                                 const uint64_t* r, const uint64_t* s, uint64_t* ticket);
+int32_t zkb_groth16_prove_collect(zkb_ctx* ctx, uint64_t ticket, uint8_t* proof_out, size_t proof_cap);
+int32_t zkb_groth16_prove_collect_partial(zkb_ctx* ctx, uint64_t ticket, uint8_t* partial_out, size_t partial_cap);
+int32_t zkb_groth16_prove_begin_async(zkb_ctx* ctx, uint64_t pk_handle, uint64_t r1cs_handle, const uint64_t* z,
+                                      uint32_t chain_mask, void* chain_dev_ptrs[3], uint64_t* chain_bytes, uint64_t* ticket);
+int32_t zkb_groth16_prove_end_async(zkb_ctx* ctx, uint64_t ticket);
+
 /* ---- witness side -------------------------------------------------
  * zkb_r1cs_check: (A z) o (B z) == C z for every constraint, on the device; z = NULL checks the resident assignment.
  *   Returns ZKB_E_UNSAT and the first violated constraint index (the interpreter's `UnsatisfiedConstraint`,

@@ -201,7 +201,8 @@ static int zko_pool_threads(void) {
   if (cached) return cached;
   int n = 1;
 #ifdef _OPENMP
-  n = omp_get_max_threads();
+  n = omp_get_num_procs();     /* NOT omp_get_max_threads(): launchers export OMP_NUM_THREADS=1 (torchrun does for every rank) */
+  { const char* e = getenv("ZKO_THREADS"); if (e && atoi(e) > 0) n = atoi(e); }
 #endif
   cpu_set_t set;
   if (sched_getaffinity(0, sizeof set, &set) == 0) { int k = CPU_COUNT(&set); if (k > 0 && k < n) n = k; }
@@ -302,12 +303,9 @@ static void domain_omega(const curve_t* c, int log_n, fe* w) {
 static void fr_scale_powers(const curve_t* c, fe* a, size_t n, const fe* g, const fe* scale) {
   /* a[i] *= scale * g^i, chunked so that it parallelises */
   const fctx* f = &c->fr;
-  int nt = 1;
-#ifdef _OPENMP
-  nt = omp_get_max_threads();
-#endif
+  int nt = zko_pool_threads();
   size_t chunk = (n + nt - 1) / nt;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(nt)
   for (int t = 0; t < nt; t++) {
     size_t lo = (size_t)t * chunk, hi = lo + chunk < n ? lo + chunk : n;
     if (lo >= hi) continue;

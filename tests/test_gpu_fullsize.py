@@ -84,6 +84,31 @@ def test_full_size_sharding_vs_trapdoor(full, oracle_c):
     ctx.pk_free(pkh)
 
 
+def test_full_size_pipelined_proofs(full, oracle_c):
+    """zkb_groth16_prove_submit / _collect with TWO 2^20 proofs in flight (what bench.py times): host-memory assignment and
+    resident assignment, different blinding scalars per proof, collected in both orders — every proof equals the trapdoor
+    prediction for its own (r, s)."""
+    ctx, c = full.ctx, full.c
+    exp = {rs: oracle_c.trapdoor_expected(full.cid, full.r1, TD, full.z, rs[0], rs[1], c.fq_bytes) for rs in ((R, S), (5, 7), (11, 13))}
+    pkh = ctx.pk_load(full.pk)
+    ctx.set_assignment(full.h, full.z)
+    t1 = ctx.prove_submit(pkh, full.h, full.z, R, S)
+    t2 = ctx.prove_submit(pkh, full.h, None, 5, 7)
+    assert ctx.prove_collect(t1) == exp[(R, S)]
+    t3 = ctx.prove_submit(pkh, full.h, full.z, 11, 13)
+    assert ctx.prove_collect(t3) == exp[(11, 13)]          # out of order
+    assert ctx.prove_collect(t2) == exp[(5, 7)]
+    # a stream of proofs, depth 2
+    pending, got = [], []
+    for i in range(6):
+        pending.append(ctx.prove_submit(pkh, full.h, None if i % 2 else full.z, R, S))
+        if len(pending) == 2:
+            got.append(ctx.prove_collect(pending.pop(0)))
+    got += [ctx.prove_collect(t) for t in pending]
+    assert got == [exp[(R, S)]] * 6
+    ctx.pk_free(pkh)
+
+
 @pytest.mark.parametrize("log_n", [15, 17])
 @pytest.mark.parametrize("dist", ["uniform", "bits"])
 def test_table_modes_vs_oracle(gpu_lib, oracle_c, log_n, dist):

@@ -211,3 +211,51 @@ def test_ntt_tiled_passes(cc, log_n, max_s):
     ctx.set_option(OPT_NTT_MAX_S, 10)
     for a, b in zip(got, legacy):
         assert np.array_equal(a, b)
+
+
+def test_pipelined_submit_collect(cc):
+    """zkb_groth16_prove_submit / _collect: two proofs in flight (different blinding scalars) give the bytes of
+    the one-at-a-time calls, in either collection order; a third submit is refused; keys and matrices of a proof in flight
+    cannot be freed; partial tickets combine through zkb_groth16_finalize."""
+    from zokrates_b200 import synthetic
+    from zokrates_b200._lib import ZkbError
+    cid, c, ctx = cc
+    r1, z1 = synthetic.make(c.name, 70, seed=5)
+    z2 = z1.copy()
+    h = ctx.r1cs_load(r1.num_constraints, r1.num_instance, r1.num_witness, r1.matrices())
+    pk = ctx.setup(h, [3, 5, 7, 11, 13, 17, 19])
+    pkh = ctx.pk_load(pk)
+    ref1 = ctx.prove(pkh, h, z1, 111, 222)
+    ref2 = ctx.prove(pkh, h, z2, 333, 444)
+    assert ref1 != ref2
+    t1 = ctx.prove_submit(pkh, h, z1, 111, 222)
+    t2 = ctx.prove_submit(pkh, h, z2, 333, 444)
+    with pytest.raises(ZkbError):
+        ctx.prove_submit(pkh, h, z1, 1, 2)
+    with pytest.raises(ZkbError):
+        ctx.pk_free(pkh)
+    with pytest.raises(ZkbError):
+        ctx.r1cs_free(h)
+    assert ctx.prove_collect(t2) == ref2
+    assert ctx.prove_collect(t1) == ref1
+    with pytest.raises(ZkbError):
+        ctx.prove_collect(t1)
+    # resident assignment + partial tickets
+    ctx.set_assignment(h, z1)
+    ta = ctx.prove_submit(pkh, h, None)
+    tb = ctx.prove_submit(pkh, h, z2)
+    pa, pb = ctx.prove_collect_partial(ta), ctx.prove_collect_partial(tb)
+    assert ctx.finalize(pkh, pa, 1, 111, 222) == ref1
+    assert ctx.finalize(pkh, pb, 1, 333, 444) == ref2
+    tp = ctx.prove_submit(pkh, h, z1)
+    with pytest.raises(ZkbError):
+        ctx.prove_collect(tp)                                    # a partial ticket has no r, s; it stays collectable
+    assert ctx.finalize(pkh, ctx.prove_collect_partial(tp), 1, 111, 222) == ref1
+    # the legacy begin / end pair and the async pair interleave with a submitted proof
+    tk = ctx.prove_submit(pkh, h, z2, 333, 444)
+    t3, ptrs, nbytes = ctx.prove_begin_async(pkh, h, z1, 7)
+    ctx.prove_end_async(t3)
+    assert ctx.prove_collect(tk) == ref2
+    assert ctx.finalize(pkh, ctx.prove_collect_partial(t3), 1, 111, 222) == ref1
+    ctx.pk_free(pkh)
+    ctx.r1cs_free(h)

@@ -26,7 +26,8 @@ SYMBOLS = [
     "zkb_msm_g1", "zkb_msm_g2", "zkb_ntt", "zkb_witness_map", "zkb_field_op", "zkb_groth16_setup",
     "zkb_groth16_setup_size", "zkb_last_timings", "zkb_launch_count", "zkb_peak_probe", "zkb_groth16_prove_begin",
     "zkb_groth16_prove_end", "zkb_groth16_finalize_prepare", "zkb_r1cs_check", "zkb_witness_eval",
-    "zkb_pk_table_info", "zkb_ctx_set_option",
+    "zkb_pk_table_info", "zkb_ctx_set_option", "zkb_groth16_prove_submit", "zkb_groth16_prove_collect",
+    "zkb_groth16_prove_collect_partial", "zkb_groth16_prove_begin_async", "zkb_groth16_prove_end_async",
 ]
 
 OPT_TABLES, OPT_TABLE_MIN_LOG, OPT_TABLE_C, OPT_Z_MODE, OPT_NTT_TILE_MIN, OPT_NTT_MAX_S = 1, 2, 3, 4, 5, 6
@@ -82,6 +83,12 @@ class Library:
         d.zkb_groth16_prove_begin.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32,
                                               C.POINTER(C.c_void_p), _u64p]
         d.zkb_groth16_prove_end.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t]
+        d.zkb_groth16_prove_submit.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, _u64p]
+        d.zkb_groth16_prove_collect.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t]
+        d.zkb_groth16_prove_collect_partial.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t]
+        d.zkb_groth16_prove_begin_async.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32,
+                                                    C.POINTER(C.c_void_p), _u64p, _u64p]
+        d.zkb_groth16_prove_end_async.argtypes = [C.c_void_p, C.c_uint64]
         d.zkb_groth16_finalize_prepare.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         d.zkb_r1cs_check.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, _u64p]
         d.zkb_witness_eval.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, _u64p]
@@ -249,6 +256,47 @@ class Context:
         out = np.zeros(self.partial_bytes, dtype=np.uint8)
         self.lib.check(self.lib.dll.zkb_groth16_prove_end(self.h, pk, r1cs, out.ctypes.data, len(out)))
         return out
+
+    # -- pipelined form: two proofs may be in flight
+    def prove_submit(self, pk, r1cs, z, r: int | None = None, s: int | None = None) -> int:
+        """Enqueue one proof (z None: the resident assignment); returns a ticket.  With r and s the ticket collects to a
+        finished proof (`prove_collect`), without to the partial sums (`prove_collect_partial`)."""
+        zp = None
+        if z is not None:
+            z = np.ascontiguousarray(z, dtype=np.uint64)
+            zp = z.ctypes.data
+        rp = sp = None
+        keep = None
+        if r is not None:
+            keep = (fr_array([r]), fr_array([s]))
+            rp, sp = keep[0].ctypes.data, keep[1].ctypes.data
+        t = C.c_uint64(0)
+        self.lib.check(self.lib.dll.zkb_groth16_prove_submit(self.h, pk, r1cs, zp, rp, sp, C.byref(t)))
+        return int(t.value)
+
+    def prove_collect(self, ticket: int) -> bytes:
+        out = np.zeros(self.proof_bytes, dtype=np.uint8)
+        self.lib.check(self.lib.dll.zkb_groth16_prove_collect(self.h, ticket, out.ctypes.data, len(out)))
+        return out.tobytes()
+
+    def prove_collect_partial(self, ticket: int) -> np.ndarray:
+        out = np.zeros(self.partial_bytes, dtype=np.uint8)
+        self.lib.check(self.lib.dll.zkb_groth16_prove_collect_partial(self.h, ticket, out.ctypes.data, len(out)))
+        return out
+
+    def prove_begin_async(self, pk, r1cs, z, chain_mask: int):
+        zp = None
+        if z is not None:
+            z = np.ascontiguousarray(z, dtype=np.uint64)
+            zp = z.ctypes.data
+        ptrs = (C.c_void_p * 3)()
+        nbytes = C.c_uint64(0)
+        t = C.c_uint64(0)
+        self.lib.check(self.lib.dll.zkb_groth16_prove_begin_async(self.h, pk, r1cs, zp, chain_mask, ptrs, C.byref(nbytes), C.byref(t)))
+        return int(t.value), [int(p or 0) for p in ptrs], int(nbytes.value)
+
+    def prove_end_async(self, ticket: int):
+        self.lib.check(self.lib.dll.zkb_groth16_prove_end_async(self.h, ticket))
 
     def finalize_prepare(self, pk, r: int, s: int):
         ra, sa = fr_array([r]), fr_array([s])

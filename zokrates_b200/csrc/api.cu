@@ -227,6 +227,38 @@ int32_t zkb_groth16_prove_end(zkb_ctx* ctx, uint64_t pk, uint64_t r1cs, uint8_t*
     ctx->eng->prove_end(pk, r1cs, partial_out);
   });
 }
+int32_t zkb_groth16_prove_begin_async(zkb_ctx* ctx, uint64_t pk, uint64_t r1cs, const uint64_t* z, uint32_t chain_mask,
+                                      void* chain_dev_ptrs[3], uint64_t* chain_bytes, uint64_t* ticket) {
+  return guard(ctx, [&] {
+    if (!chain_dev_ptrs || !chain_bytes || !ticket) throw Error(ZKB_E_ARG, "null argument");
+    *ticket = ctx->eng->prove_begin_async(pk, r1cs, z, chain_mask, chain_dev_ptrs, chain_bytes);
+  });
+}
+int32_t zkb_groth16_prove_end_async(zkb_ctx* ctx, uint64_t ticket) {
+  return guard(ctx, [&] { ctx->eng->prove_end_async(ticket); });
+}
+int32_t zkb_groth16_prove_submit(zkb_ctx* ctx, uint64_t pk, uint64_t r1cs, const uint64_t* z, const uint64_t* r, const uint64_t* s,
+                                 uint64_t* ticket) {
+  return guard(ctx, [&] {
+    if (!ticket || (!r) != (!s)) throw Error(ZKB_E_ARG, "null argument");
+    *ticket = ctx->eng->prove_submit(pk, r1cs, z, r, s);
+  });
+}
+int32_t zkb_groth16_prove_collect(zkb_ctx* ctx, uint64_t ticket, uint8_t* proof_out, size_t cap) {
+  return guard(ctx, [&] {
+    if (!proof_out) throw Error(ZKB_E_ARG, "null argument");
+    check_proof_cap(ctx, cap);
+    ctx->eng->prove_collect(ticket, proof_out);
+  });
+}
+int32_t zkb_groth16_prove_collect_partial(zkb_ctx* ctx, uint64_t ticket, uint8_t* partial_out, size_t cap) {
+  return guard(ctx, [&] {
+    uint64_t sz[4];
+    ctx->eng->sizes(sz);
+    if (!partial_out || cap < sz[3]) throw Error(ZKB_E_ARG, "partial_out too small");
+    ctx->eng->prove_collect_partial(ticket, partial_out);
+  });
+}
 int32_t zkb_groth16_finalize_prepare(zkb_ctx* ctx, uint64_t pk, const uint64_t* r, const uint64_t* s) {
   return guard(ctx, [&] {
     if (!r || !s) throw Error(ZKB_E_ARG, "null argument");

@@ -425,7 +425,7 @@ class Engine : public EngineBase {
     uint32_t log_n = 0;
     DevBuf<uint32_t> rowptr[3], col[3];
     DevBuf<Fr> val[3];
-    DevBuf<Fr> z_canon, z_mont, a, b, c, h;
+    DevBuf<Fr> z_canon, z_mont;     // resident assignment (zkb_r1cs_set_assignment / zkb_witness_eval); per-proof vectors live in ProofSlot
     bool has_z = false;
     bool sparse_z = false;  // most assignment values are tiny (bits): the z MSMs are cheap, prefer the per-window bucket sets (shallower reductions)
     // host copies kept for setup (CSC transposition) — small relative to the device data
@@ -471,14 +471,18 @@ class Engine : public EngineBase {
       convert(r->val[k].p, r->val[k].p, 0, nnz);
     }
     r->z_canon.alloc(r->m); r->z_mont.alloc(r->m);
-    r->a.alloc(n); r->b.alloc(n); r->c.alloc(n); r->h.alloc(n);
+    (void)n;
     domain(lg);
     stream_sync(st_);
     uint64_t h = next_handle_++;
     r1cs_[h] = std::move(r);
     return h;
   }
-  void r1cs_free(uint64_t h) override { r1cs_.erase(h); }
+  void r1cs_free(uint64_t h) override {
+    for (auto& sl : slots_)
+      if (sl.state != 0 && sl.r1cs == h) throw Error(ZKB_E_ARG, "a proof that uses this R1CS is in flight (collect it first)");
+    r1cs_.erase(h);
+  }
 
   void set_assignment(uint64_t h, const uint64_t* z) override {
     R1cs& r = get_r1cs(h);
@@ -488,18 +492,70 @@ class Engine : public EngineBase {
     r.sparse_z = assignment_is_sparse(z, r.m);
   }
 
+  // ------------------------------------------------------------------------------ per-proof state
+  // Everything one proof writes on the device lives in a ProofSlot, and there are two of them: while the host finishes
+  // proof i (the last few hundred point additions of every MSM, the final combination, the multi-GPU gather) the GPU
+  // already runs proof i + 1 — its digit plans and accumulate kernels overlap the latency-bound reduction tails of
+  // proof i.  Read-only state (key shards, matrices, domain tables) is shared.
+  // the four scalar multiplications that only need (pk, r, s): computed on host threads while the GPU works
+  struct FixedMults {
+    HG1X rd, sd, rsd;
+    HG2X sd2;
+  };
+  struct MsmWs {
+    DevBuf<uint8_t> buckets, val[2], tree[4];
+    DevBuf<uint32_t> key[2];
+    Stream tail;          // high-priority side stream for accum2 / bit sums
+    Event acc_done, tail_done;
+    bool has_stream = false;
+    // filled by msm_tail: the bit-sum reduction ran `tree_lvls` levels and left `tree_cnt` block totals per window
+    uint32_t tree_cnt = 1, tree_lvls = 0;
+    size_t out_entries = 0;   // XYZZ entries of the result slot the host has to read: (1 + 3 * tree_lvls) * W * tree_cnt
+    void destroy() { if (has_stream) { stream_destroy(tail); has_stream = false; } acc_done.destroy(); tail_done.destroy(); }
+  };
+  struct ProofSlot {
+    DevBuf<Fr> z_canon, z_mont, a, b, c, h;   // assignment (when it came from the host), its Montgomery image, witness-map vectors
+    const Fr* z_src = nullptr;                // canonical assignment this proof reads (own upload or the resident one)
+    bool sparse_z = false;
+    MsmPlan plan_z, plan_h;
+    MsmWs ws[5];                              // h, l, a, b1, b2
+    DevBuf<uint8_t> d_win;                    // result slots of the five MSMs
+    HostBuf hw;                               // pinned landing zone of the same
+    std::unique_ptr<StageTimer> tm, tm2;
+    Event ev_z_ready, ev_h_ready, ev_chains_done, done;
+    Stream fin; bool has_fin = false;         // waits for the five tails and copies the results out, off the main stream
+    uint64_t pk = 0, r1cs = 0, ticket = 0;
+    int state = 0;                            // 0 free, 1 begun (assignment MSMs enqueued), 2 fully enqueued (collectable)
+    bool has_rs = false;
+    uint32_t r[8], s[8];
+    std::future<FixedMults> fm;
+    void destroy() {
+      for (auto& w : ws) w.destroy();
+      ev_z_ready.destroy(); ev_h_ready.destroy(); ev_chains_done.destroy(); done.destroy();
+      if (has_fin) { stream_destroy(fin); has_fin = false; }
+    }
+  };
+  static constexpr int NUM_SLOTS = 2;
+  ProofSlot slots_[NUM_SLOTS];
+  uint64_t next_ticket_ = 1;
+  void slot_vectors(ProofSlot& sl, const R1cs& r) {
+    const size_t n = (size_t)1 << r.log_n;
+    sl.z_canon.ensure(r.m); sl.z_mont.ensure(r.m);
+    sl.a.ensure(n); sl.b.ensure(n); sl.c.ensure(n); sl.h.ensure(n);
+  }
+
   // h (canonical, natural order) = witness_map(z)   [device-resident]
   // The witness map in two halves so that several GPUs can share it (zkb_groth16_prove_begin / _end):
   //   chains: for every k in `mask`: v_k = coset_fft(ifft(M_k z)) — three independent SpMV + 2 transforms (a, b, c)
   //   finish: h = coset_ifft((a∘b − c) / Z)  — needs all three chains
-  void wm_chains(R1cs& r, uint32_t mask, StageTimer& tm) {
+  void wm_chains(R1cs& r, ProofSlot& sl, uint32_t mask, StageTimer& tm) {
     DomainT& d = domain(r.log_n);
     const uint32_t lg = r.log_n;
     const size_t n = (size_t)1 << lg;
     tm.begin("witness_map_chains");
-    convert(r.z_canon.p, r.z_mont.p, 0, r.m);
-    Fr* vec[3] = {r.a.p, r.b.p, r.c.p};
-    const Fr* zm = r.z_mont.p;
+    convert(sl.z_src, sl.z_mont.p, 0, r.m);
+    Fr* vec[3] = {sl.a.p, sl.b.p, sl.c.p};
+    const Fr* zm = sl.z_mont.p;
     const Fr* t1 = d.cos_fwd.p;
     for (int k = 0; k < 3; k++) {
       if (!((mask >> k) & 1u)) continue;
@@ -510,31 +566,24 @@ class Engine : public EngineBase {
       const uint32_t N = (uint32_t)r.N;
       dev_zero(st_, out + r.N, (n - r.N) * FRB);
       launch<k_spmv>(st_, r.N, ZKB_LAMBDA(size_t t) { spmv_body<Fr>(rp, cl, vl, zm, out, N, (uint32_t)t); });
-      if (k == 0) d2d(st_, r.a.p + r.N, r.z_mont.p, r.ni * FRB);  // a[N + j] = z[j] for the instance variables
+      if (k == 0) d2d(st_, sl.a.p + r.N, sl.z_mont.p, r.ni * FRB);  // a[N + j] = z[j] for the instance variables
       ntt_dif(out, d.tw_inv.p, lg);
       ntt_dit(out, d.tw_fwd.p, lg, t1);   // coset shift (g^k / n at the bit-reversed position) fused into the first pass
     }
     tm.end();
   }
-  void wm_finish(R1cs& r, StageTimer& tm) {
+  void wm_finish(R1cs& r, ProofSlot& sl, StageTimer& tm) {
     DomainT& d = domain(r.log_n);
     const uint32_t lg = r.log_n;
     const size_t n = (size_t)1 << lg;
     tm.begin("witness_map_finish");
-    Fr* pa = r.a.p; const Fr* pb = r.b.p; const Fr* pc = r.c.p;
+    Fr* pa = sl.a.p; const Fr* pb = sl.b.p; const Fr* pc = sl.c.p;
     Fr zinv = d.zinv;
     launch<k_qap_pointwise>(st_, n, ZKB_LAMBDA(size_t t) { qap_pointwise_body<Fr>(pa, pb, pc, zinv, (uint32_t)n, (uint32_t)t); });
     ntt_dif(pa, d.tw_inv.p, lg);
-    Fr* ph = r.h.p;
+    Fr* ph = sl.h.p;
     const Fr* t2 = d.cos_inv.p;
     launch<k_ntt_brev>(st_, n, ZKB_LAMBDA(size_t t) { ntt_brev_copy_body<Fr>(pa, ph, t2, lg, 1, (uint32_t)t); });
-    tm.end();
-  }
-  // h (canonical, natural order) = witness_map(z)   [device-resident]
-  void witness_map_dev(R1cs& r, StageTimer& tm) {
-    tm.begin("witness_map");
-    wm_chains(r, 7, tm);
-    wm_finish(r, tm);
     tm.end();
   }
 
@@ -542,10 +591,17 @@ class Engine : public EngineBase {
     R1cs& r = get_r1cs(h);
     const size_t n = (size_t)1 << r.log_n;
     if (cap < n) throw Error(ZKB_E_ARG, "h_out too small");
+    ProofSlot& sl = slots_[0];
+    if (sl.state != 0) throw Error(ZKB_E_ARG, "a proof is in flight on this context");
+    slot_vectors(sl, r);
     StageTimer tm(st_);
-    h2d(st_, r.z_canon.p, z, r.m * FRB);
-    witness_map_dev(r, tm);
-    d2h(st_, h_out, r.h.p, n * FRB);
+    h2d(st_, sl.z_canon.p, z, r.m * FRB);
+    sl.z_src = sl.z_canon.p;
+    tm.begin("witness_map");
+    wm_chains(r, sl, 7, tm);
+    wm_finish(r, sl, tm);
+    tm.end();
+    d2h(st_, h_out, sl.h.p, n * FRB);
     stream_sync(st_);
     tm.collect(timings);
   }
@@ -645,23 +701,10 @@ class Engine : public EngineBase {
     launch<k_msm_scatter>(st_, total, ZKB_LAMBDA(size_t t) { msm_scatter_body(sh, nviews, skip, dg, of, cu, so, t); });
   }
 
-  // per-MSM scratch so that the latency-bound tails of different MSMs can overlap
-  struct MsmWs {
-    DevBuf<uint8_t> buckets, val[2], tree[4];
-    DevBuf<uint32_t> key[2];
-    Stream tail;          // high-priority side stream for accum2 / tree
-    Event acc_done, tail_done;
-    bool has_stream = false;
-    // filled by msm_tail: the bit-sum reduction ran `tree_lvls` levels and left `tree_cnt` block totals per window
-    uint32_t tree_cnt = 1, tree_lvls = 0;
-    size_t out_entries = 0;   // XYZZ entries of the result slot the host has to read: (1 + 3 * tree_lvls) * W * tree_cnt
-  };
-  static constexpr int NUM_WS = 6;   // h, l, a, b1, b2, misc
-  MsmWs ws_[NUM_WS];
+  MsmWs ws_misc_;       // standalone zkb_msm_g1 / g2
   // witness map + h-plan run on their own stream underneath the z-dependent MSMs
   Stream wm_stream_;
   bool has_wm_stream_ = false;
-  Event ev_z_ready_, ev_h_ready_;
   struct StreamScope {  // temporarily redirect every helper that launches on st_
     Stream& ref; Stream saved;
     StreamScope(Stream& r, Stream s) : ref(r), saved(r) { ref = s; }
@@ -672,9 +715,10 @@ class Engine : public EngineBase {
     return ws.tail;
   }
   ~Engine() override {
-    for (auto& w : ws_) { if (w.has_stream) stream_destroy(w.tail); w.acc_done.destroy(); w.tail_done.destroy(); }
+    if (prepared_.fut.valid()) prepared_.fut.wait();
+    for (auto& sl : slots_) { if (sl.fm.valid()) sl.fm.wait(); sl.destroy(); }
+    ws_misc_.destroy();
     if (has_wm_stream_) stream_destroy(wm_stream_);
-    ev_z_ready_.destroy(); ev_h_ready_.destroy();
   }
 
   // phase 1 (main stream): bucket accumulation of one MSM.  Throughput-bound (INT32 multiply pipe).
@@ -1026,14 +1070,16 @@ class Engine : public EngineBase {
     out[0] = p.ni; out[1] = p.m; out[2] = p.hl; out[3] = p.ll;
   }
   void pk_free(uint64_t h) override {
+    for (auto& sl : slots_) {
+      if (sl.state != 0 && sl.pk == h) throw Error(ZKB_E_ARG, "a proof that uses this key is in flight (collect it first)");
+      if (sl.fm.valid()) sl.fm.wait();     // a finished proof's host multiplications may still read the key's fixed points
+    }
     if (prepared_.pk == h) { if (prepared_.fut.valid()) prepared_.fut.wait(); prepared_.pk = 0; }
     pks_.erase(h);
   }
 
   // ------------------------------------------------------------------------------ prove
-  MsmPlan plan_z_, plan_h_;
   DevBuf<Fr> scratch_a_, scratch_b_;
-  DevBuf<uint8_t> d_win_;
   static constexpr uint32_t MAXW = 1024;  // result slot entries per MSM: (1 + 3 levels) * W * tree_cnt <= 19 * 32
 
   struct HostPartial {  // same layout as Partial
@@ -1051,148 +1097,243 @@ class Engine : public EngineBase {
     return cnt && small * 2 > cnt;
   }
 
-  bool z_window_mode(const R1cs& r) const { return opts.z_mode == 2 || (opts.z_mode == 0 && r.sparse_z); }
+  bool z_window_mode(bool sparse) const { return opts.z_mode == 2 || (opts.z_mode == 0 && sparse); }
 
-  // One proof's device work in two calls so that the host can exchange witness-map chains between them:
-  //   begin: upload z, start the chains of `chain_mask` on the witness-map stream, the z plan and the four z-MSMs on the
-  //          main stream; if some chains are left to other ranks, wait until this rank's chains are complete
-  //   end  : (all three chain buffers hold coset evaluations) finish the witness map, h plan, h-MSM, tails, host finish
-  // zkb_groth16_prove_partial = begin(all chains) + end.
-  std::unique_ptr<StageTimer> tm_, tm2_;
-  uint64_t open_pk_ = 0, open_r1cs_ = 0;
-  Event ev_chains_done_;
+  // One proof's device work is ENQUEUED in two steps and COLLECTED in a third, so that (a) the host can exchange witness-map
+  // chains between the ranks in the middle and (b) two proofs can be in flight (ProofSlot):
+  //   begin  : upload z, start the chains of `chain_mask` on the witness-map stream, the z plan and the four z-MSMs on the
+  //            main stream; if some chains are left to other ranks, wait until this rank's chains are complete
+  //   finish : (all three chain buffers hold coset evaluations) rest of the witness map, h plan, h-MSM; a side stream waits
+  //            for the five reduction tails and copies their results to pinned host memory.  Returns without synchronising.
+  //   collect: waits for that copy, runs the host part of the reductions, returns the five partial sums.
+  // zkb_groth16_prove_partial = begin(all chains) + finish + collect;  zkb_groth16_prove_submit = begin + finish.
+  uint64_t open_ticket_ = 0;     // the proof opened by the legacy zkb_groth16_prove_begin
 
-  void prove_begin(uint64_t pkh, uint64_t rh, const uint64_t* z, uint32_t chain_mask, void* chain_ptrs[3],
-                   uint64_t* chain_bytes) override {
+  ProofSlot& slot_of(uint64_t ticket) {
+    for (auto& sl : slots_)
+      if (sl.state != 0 && sl.ticket == ticket) return sl;
+    throw Error(ZKB_E_ARG, "unknown proof ticket");
+  }
+  Stream fin_stream(ProofSlot& sl) {
+    if (!sl.has_fin) { sl.fin = stream_create_high_priority(); sl.has_fin = true; }
+    return sl.fin;
+  }
+
+  uint64_t slot_begin(uint64_t pkh, uint64_t rh, const uint64_t* z, uint32_t chain_mask) {
     Pk& pk = get_pk(pkh);
     R1cs& r = get_r1cs(rh);
     const size_t n = (size_t)1 << r.log_n;
     if (pk.m != r.m || pk.ni != r.ni) throw Error(ZKB_E_ARG, "proving key does not match the R1CS (variable counts)");
     if (pk.hl + 1 != n) throw Error(ZKB_E_ARG, "proving key does not match the R1CS (domain size)");
     if (chain_mask > 7) throw Error(ZKB_E_ARG, "chain_mask");
-    if (open_pk_) throw Error(ZKB_E_ARG, "a proof is already open on this context (call zkb_groth16_prove_end)");
-    tm_.reset(new StageTimer(st_));
-    StageTimer& tm = *tm_;
+    ProofSlot* free_slot = nullptr;
+    for (auto& c : slots_) if (c.state == 0) { free_slot = &c; break; }
+    if (!free_slot) throw Error(ZKB_E_ARG, "two proofs are already in flight on this context (collect one first)");
+    ProofSlot& sl = *free_slot;
+    if (!z && !r.has_z) throw Error(ZKB_E_ARG, "no resident assignment");
+    slot_vectors(sl, r);
+    sl.tm.reset(new StageTimer(st_));
+    StageTimer& tm = *sl.tm;
     if (z) {
       tm.begin("h2d_z");
-      h2d(st_, r.z_canon.p, z, r.m * FRB);
+      h2d(st_, sl.z_canon.p, z, r.m * FRB);
       tm.end();
-      r.has_z = true;
-      r.sparse_z = assignment_is_sparse(z, r.m);
-    } else if (!r.has_z) {
-      throw Error(ZKB_E_ARG, "no resident assignment");
+      sl.z_src = sl.z_canon.p;
+      sl.sparse_z = assignment_is_sparse(z, r.m);
+    } else {
+      sl.z_src = r.z_canon.p;
+      sl.sparse_z = r.sparse_z;
     }
     const size_t slot1 = MAXW * sizeof(G1X), slot2 = MAXW * sizeof(G2X);
-    d_win_.ensure(4 * slot1 + slot2);
-    G1X* w_l = (G1X*)(d_win_.p + slot1);
-    G1X* w_a = (G1X*)(d_win_.p + 2 * slot1);
-    G1X* w_b1 = (G1X*)(d_win_.p + 3 * slot1);
-    G2X* w_b2 = (G2X*)(d_win_.p + 4 * slot1);
+    sl.d_win.ensure(4 * slot1 + slot2);
+    sl.hw.ensure(4 * slot1 + slot2);
+    G1X* w_l = (G1X*)(sl.d_win.p + slot1);
+    G1X* w_a = (G1X*)(sl.d_win.p + 2 * slot1);
+    G1X* w_b1 = (G1X*)(sl.d_win.p + 3 * slot1);
+    G2X* w_b2 = (G2X*)(sl.d_win.p + 4 * slot1);
     // The witness map (3 SpMV, 7 NTT, latency/bandwidth-bound at this size) and the h digit plan go to a second
-    // stream and fill the multiply-pipe bubbles of the z-dependent MSMs running on the main stream.
-    if (!has_wm_stream_) {
-      // high priority: its small kernels slot in between the blocks of the big accumulate kernels
-      wm_stream_ = stream_create_high_priority();
-      has_wm_stream_ = true;
-    }
-    // The witness map starts at once on its own stream.  Letting the z plan run alone first (ZKB_WM_EARLY=0) shortens the
-    // plan from 2.3 to 0.8 ms but the displaced witness-map work then slows the accumulate kernels by the same amount
-    // (measured 21.03 vs 20.97 ms, profiles/r01_tuning_log.md): the proof is work-bound, not schedule-bound.
-    const bool wm_early = true;
-    tm2_.reset(new StageTimer(wm_stream_));
-    StageTimer& tm2 = *tm2_;
-    auto enqueue_chains = [&]() {
-      ev_z_ready_.record(st_);
+    // (high-priority) stream and fill the multiply-pipe bubbles of the z-dependent MSMs running on the main stream.
+    if (!has_wm_stream_) { wm_stream_ = stream_create_high_priority(); has_wm_stream_ = true; }
+    sl.tm2.reset(new StageTimer(wm_stream_));
+    {
+      sl.ev_z_ready.record(st_);
       StreamScope sc(st_, wm_stream_);
-      ev_z_ready_.wait(st_);
-      wm_chains(r, chain_mask, tm2);
-      ev_chains_done_.record(st_);
-    };
-    if (wm_early) enqueue_chains();
+      sl.ev_z_ready.wait(st_);
+      wm_chains(r, sl, chain_mask, *sl.tm2);
+      sl.ev_chains_done.record(st_);
+    }
     tm.begin("msm_plan_z");
-    plan_build(plan_z_, r.z_canon.p + 1 + pk.lo, pk.hi - pk.lo, 3, pk.skip.p, z_window_mode(r) ? 0 : pk.pre_cz);
+    plan_build(sl.plan_z, sl.z_src + 1 + pk.lo, pk.hi - pk.lo, 3, pk.skip.p, z_window_mode(sl.sparse_z) ? 0 : pk.pre_cz);
     tm.end();
-    if (!wm_early) enqueue_chains();
-    msm_exec<Fq2>(plan_z_, pk.b2.p, w_b2, ws_[4], &tm, "accum1_g2_b2", 2, "tail_g2_b2");
-    msm_exec<Fq>(plan_z_, pk.l.p, w_l, ws_[1], &tm, "accum1_g1_l", 0, "tail_g1_l");
-    msm_exec<Fq>(plan_z_, pk.a.p, w_a, ws_[2], &tm, "accum1_g1_a", 1, "tail_g1_a");
-    msm_exec<Fq>(plan_z_, pk.b1.p, w_b1, ws_[3], &tm, "accum1_g1_b1", 2, "tail_g1_b1");
-    open_pk_ = pkh; open_r1cs_ = rh;
-    if (chain_ptrs) { chain_ptrs[0] = r.a.p; chain_ptrs[1] = r.b.p; chain_ptrs[2] = r.c.p; }
-    if (chain_bytes) *chain_bytes = n * FRB;
+    msm_exec<Fq2>(sl.plan_z, pk.b2.p, w_b2, sl.ws[4], &tm, "accum1_g2_b2", 2, "tail_g2_b2");
+    msm_exec<Fq>(sl.plan_z, pk.l.p, w_l, sl.ws[1], &tm, "accum1_g1_l", 0, "tail_g1_l");
+    msm_exec<Fq>(sl.plan_z, pk.a.p, w_a, sl.ws[2], &tm, "accum1_g1_a", 1, "tail_g1_a");
+    msm_exec<Fq>(sl.plan_z, pk.b1.p, w_b1, sl.ws[3], &tm, "accum1_g1_b1", 2, "tail_g1_b1");
+    sl.pk = pkh; sl.r1cs = rh; sl.ticket = next_ticket_++; sl.state = 1; sl.has_rs = false;
     // chains left to other ranks: the caller exchanges buffers next, so this rank's chains must be complete in memory
     if (chain_mask != 7) stream_sync(wm_stream_);
+    return sl.ticket;
   }
 
-  void prove_end(uint64_t pkh, uint64_t rh, uint8_t* partial_out) override {
-    if (!open_pk_ || open_pk_ != pkh || open_r1cs_ != rh) throw Error(ZKB_E_ARG, "zkb_groth16_prove_end without a matching prove_begin");
-    open_pk_ = 0; open_r1cs_ = 0;
-    Pk& pk = get_pk(pkh);
-    R1cs& r = get_r1cs(rh);
-    StageTimer& tm = *tm_;
-    StageTimer& tm2 = *tm2_;
-    const size_t slot1 = MAXW * sizeof(G1X), slot2 = MAXW * sizeof(G2X);
-    G1X* w_h = (G1X*)d_win_.p;
+  void slot_finish(ProofSlot& sl) {
+    if (sl.state != 1) throw Error(ZKB_E_ARG, "proof is not open");
+    Pk& pk = get_pk(sl.pk);
+    R1cs& r = get_r1cs(sl.r1cs);
+    StageTimer& tm = *sl.tm;
+    StageTimer& tm2 = *sl.tm2;
+    const size_t slot1 = MAXW * sizeof(G1X);
+    G1X* w_h = (G1X*)sl.d_win.p;
     {
       StreamScope sc(st_, wm_stream_);
-      wm_finish(r, tm2);
+      wm_finish(r, sl, tm2);
       tm2.begin("msm_plan_h");
-      plan_build(plan_h_, r.h.p + pk.hlo, pk.hhi - pk.hlo, 1, nullptr, pk.pre_ch);
+      plan_build(sl.plan_h, sl.h.p + pk.hlo, pk.hhi - pk.hlo, 1, nullptr, pk.pre_ch);
       tm2.end();
-      ev_h_ready_.record(st_);
+      sl.ev_h_ready.record(st_);
     }
     tm.begin("wait_h");
-    ev_h_ready_.wait(st_);
+    sl.ev_h_ready.wait(st_);
     tm.end();
-    msm_exec<Fq>(plan_h_, pk.h.p, w_h, ws_[0], &tm, "accum1_g1_h", 0, "tail_g1_h");
-    tm.begin("tails_wait");
-    for (int k = 0; k < 5; k++) ws_[k].tail_done.wait(st_);
-    tm.end();
-    std::vector<uint8_t> hw(4 * slot1 + slot2);
-    tm.begin("d2h_windows");
+    msm_exec<Fq>(sl.plan_h, pk.h.p, w_h, sl.ws[0], &tm, "accum1_g1_h", 0, "tail_g1_h");
+    // the rest happens OFF the main stream, so the next proof's plan and accumulate kernels follow at once
+    Stream fs = fin_stream(sl);
+    sl.ws[0].acc_done.wait(fs);
+    size_t span = tm.begin_on(fs, "tails_wait");
+    for (int k = 0; k < 5; k++) sl.ws[k].tail_done.wait(fs);
+    tm.end_on(fs, span);
+    span = tm.begin_on(fs, "d2h_windows");
     {  // only the entries each tail produced (tree_cnt block totals + the pending bit-sum arrays)
       const size_t offs[5] = {0, slot1, 2 * slot1, 3 * slot1, 4 * slot1};
       const size_t esz[5] = {sizeof(G1X), sizeof(G1X), sizeof(G1X), sizeof(G1X), sizeof(G2X)};
-      const MsmPlan* pls[5] = {&plan_h_, &plan_z_, &plan_z_, &plan_z_, &plan_z_};
+      const MsmPlan* pls[5] = {&sl.plan_h, &sl.plan_z, &sl.plan_z, &sl.plan_z, &sl.plan_z};
       for (int k = 0; k < 5; k++)
-        if (pls[k]->sh.n) d2h(st_, hw.data() + offs[k], d_win_.p + offs[k], ws_[k].out_entries * esz[k]);
+        if (pls[k]->sh.n) d2h(fs, sl.hw.p + offs[k], sl.d_win.p + offs[k], sl.ws[k].out_entries * esz[k]);
     }
-    tm.end();
-    stream_sync(st_);
-    tm.collect(timings);
-    {
+    tm.end_on(fs, span);
+    sl.done.record(fs);
+    sl.state = 2;
+  }
+
+  void slot_collect(ProofSlot& sl, uint8_t* partial_out) {
+    if (sl.state != 2) throw Error(ZKB_E_ARG, "proof is not fully enqueued (zkb_groth16_prove_end first)");
+    const size_t slot1 = MAXW * sizeof(G1X);
+    try {
+      sl.done.sync();             // everything this proof enqueued on any stream precedes `done`
+      sl.tm->collect(timings);
       std::vector<std::pair<const char*, double>> t2;
-      tm2.collect(t2);
+      sl.tm2->collect(t2);
       for (auto& e : t2) timings.push_back(e);
+    } catch (...) {
+      sl.state = 0;
+      throw;
     }
     HostPartial hp;
+    const uint8_t* hw = sl.hw.p;
     const auto t_host0 = std::chrono::steady_clock::now();
     // five independent host reductions (a few hundred point additions each): one thread per MSM
     auto hor1 = [&](size_t k, const MsmPlan& pl) {
-      return pl.sh.n ? host_finish<HG1X>((const HG1X*)(hw.data() + k * slot1), pl, ws_[k]) : HG1X::identity();
+      return pl.sh.n ? host_finish<HG1X>((const HG1X*)(hw + k * slot1), pl, sl.ws[k]) : HG1X::identity();
     };
     auto f_b2 = std::async(std::launch::async, [&] {
-      return plan_z_.sh.n ? host_finish<HG2X>((const HG2X*)(hw.data() + 4 * slot1), plan_z_, ws_[4]) : HG2X::identity();
+      return sl.plan_z.sh.n ? host_finish<HG2X>((const HG2X*)(hw + 4 * slot1), sl.plan_z, sl.ws[4]) : HG2X::identity();
     });
-    auto f_h = std::async(std::launch::async, [&] { return hor1(0, plan_h_); });
-    auto f_l = std::async(std::launch::async, [&] { return hor1(1, plan_z_); });
-    auto f_a = std::async(std::launch::async, [&] { return hor1(2, plan_z_); });
-    hp.b1 = hor1(3, plan_z_);
+    auto f_h = std::async(std::launch::async, [&] { return hor1(0, sl.plan_h); });
+    auto f_l = std::async(std::launch::async, [&] { return hor1(1, sl.plan_z); });
+    auto f_a = std::async(std::launch::async, [&] { return hor1(2, sl.plan_z); });
+    hp.b1 = hor1(3, sl.plan_z);
     hp.h = f_h.get(); hp.l = f_l.get(); hp.a = f_a.get(); hp.b2 = f_b2.get();
     timings.push_back({"host_tree_finish", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count()});
     memcpy(partial_out, &hp, sizeof hp);
+    sl.state = 0;
+  }
+
+  // ---- legacy two-call form (one open proof), used by the multi-GPU chain exchange
+  void prove_begin(uint64_t pkh, uint64_t rh, const uint64_t* z, uint32_t chain_mask, void* chain_ptrs[3],
+                   uint64_t* chain_bytes) override {
+    if (open_ticket_) throw Error(ZKB_E_ARG, "a proof is already open on this context (call zkb_groth16_prove_end)");
+    const uint64_t t = slot_begin(pkh, rh, z, chain_mask);
+    open_ticket_ = t;
+    ProofSlot& sl = slot_of(t);
+    if (chain_ptrs) { chain_ptrs[0] = sl.a.p; chain_ptrs[1] = sl.b.p; chain_ptrs[2] = sl.c.p; }
+    if (chain_bytes) *chain_bytes = ((size_t)1 << get_r1cs(rh).log_n) * FRB;
+  }
+  void prove_end(uint64_t pkh, uint64_t rh, uint8_t* partial_out) override {
+    if (!open_ticket_) throw Error(ZKB_E_ARG, "zkb_groth16_prove_end without a matching prove_begin");
+    ProofSlot& sl = slot_of(open_ticket_);
+    if (sl.pk != pkh || sl.r1cs != rh) throw Error(ZKB_E_ARG, "zkb_groth16_prove_end without a matching prove_begin");
+    open_ticket_ = 0;
+    try {
+      slot_finish(sl);
+    } catch (...) {
+      sl.state = 0;
+      throw;
+    }
+    slot_collect(sl, partial_out);
+  }
+  // ---- pipelined form: enqueue now, collect later (two proofs may be in flight)
+  uint64_t prove_begin_async(uint64_t pkh, uint64_t rh, const uint64_t* z, uint32_t chain_mask, void* chain_ptrs[3],
+                             uint64_t* chain_bytes) override {
+    const uint64_t t = slot_begin(pkh, rh, z, chain_mask);
+    ProofSlot& sl = slot_of(t);
+    if (chain_ptrs) { chain_ptrs[0] = sl.a.p; chain_ptrs[1] = sl.b.p; chain_ptrs[2] = sl.c.p; }
+    if (chain_bytes) *chain_bytes = ((size_t)1 << get_r1cs(rh).log_n) * FRB;
+    return t;
+  }
+  void prove_end_async(uint64_t ticket) override {
+    ProofSlot& sl = slot_of(ticket);
+    try {
+      slot_finish(sl);
+    } catch (...) {
+      sl.state = 0;
+      throw;
+    }
+  }
+  uint64_t prove_submit(uint64_t pkh, uint64_t rh, const uint64_t* z, const uint64_t* r, const uint64_t* s) override {
+    const uint64_t t = slot_begin(pkh, rh, z, 7);
+    ProofSlot& sl = slot_of(t);
+    try {
+      slot_finish(sl);
+    } catch (...) {
+      sl.state = 0;
+      throw;
+    }
+    if (r && s) {
+      // r*d1, s*d1, rs*d1, s*d2 need nothing from the GPU: host threads compute them underneath the kernels
+      memcpy(sl.r, r, 32); memcpy(sl.s, s, 32);
+      sl.has_rs = true;
+      const Pk* pkp = &get_pk(pkh);
+      const uint32_t* rr = sl.r; const uint32_t* ss = sl.s;
+      sl.fm = std::async(std::launch::async, [pkp, rr, ss] { return fixed_mults(*pkp, rr, ss); });
+    }
+    return t;
+  }
+  void prove_collect_partial(uint64_t ticket, uint8_t* partial_out) override {
+    ProofSlot& sl = slot_of(ticket);
+    if (sl.fm.valid()) sl.fm.wait();
+    slot_collect(sl, partial_out);
+  }
+  void prove_collect(uint64_t ticket, uint8_t* proof_out) override {
+    ProofSlot& sl = slot_of(ticket);
+    if (!sl.has_rs) throw Error(ZKB_E_ARG, "zkb_groth16_prove_collect needs r and s at submit time");
+    const Pk& pk = get_pk(sl.pk);
+    std::vector<uint8_t> partial(sizeof(HostPartial));
+    try {
+      slot_collect(sl, partial.data());
+    } catch (...) {
+      if (sl.fm.valid()) sl.fm.wait();
+      throw;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    FixedMults fm = sl.fm.get();
+    finalize_with(pk, fm, partial.data(), 1, sl.r, sl.s, proof_out);
+    timings.push_back({"host_final_combine", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()});
   }
 
   void prove_partial(uint64_t pkh, uint64_t rh, const uint64_t* z, uint8_t* partial_out) override {
-    prove_begin(pkh, rh, z, 7, nullptr, nullptr);
-    prove_end(pkh, rh, partial_out);
+    const uint64_t t = prove_submit(pkh, rh, z, nullptr, nullptr);
+    slot_collect(slot_of(t), partial_out);
   }
 
-  // the four scalar multiplications that only need (pk, r, s): computed while the GPU works
-  struct FixedMults {
-    HG1X rd, sd, rsd;
-    HG2X sd2;
-  };
   static FixedMults fixed_mults(const Pk& pk, const uint32_t* r, const uint32_t* s) {
     FixedMults f;
     HFr a, b;
@@ -1271,24 +1412,12 @@ class Engine : public EngineBase {
 
   void prove_full(uint64_t pkh, uint64_t rh, const uint64_t* z, const uint64_t* r, const uint64_t* s,
                   uint8_t* proof_out) override {
-    Pk& pk = get_pk(pkh);
-    // r*d1, s*d1, rs*d1, s*d2 need nothing from the GPU: run them on a host thread under the kernels
-    auto fut = std::async(std::launch::async, [&pk, r, s] { return fixed_mults(pk, (const uint32_t*)r, (const uint32_t*)s); });
-    std::vector<uint8_t> partial(sizeof(HostPartial));
-    try {
-      prove_partial(pkh, rh, z, partial.data());
-    } catch (...) {
-      fut.wait();
-      throw;
-    }
-    const auto t0 = std::chrono::steady_clock::now();
-    FixedMults fm = fut.get();
-    finalize_with(pk, fm, partial.data(), 1, (const uint32_t*)r, (const uint32_t*)s, proof_out);
-    timings.push_back({"host_final_combine", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()});
+    const uint64_t t = prove_submit(pkh, rh, z, r, s);
+    prove_collect(t, proof_out);
   }
 
   // ------------------------------------------------------------------------------ standalone MSM (tests / microbench)
-  DevBuf<uint8_t> msm_pts_;
+  DevBuf<uint8_t> msm_pts_, d_win_;
   DevBuf<Fr> msm_scalars_;
   MsmPlan plan_misc_;
 
@@ -1310,14 +1439,14 @@ class Engine : public EngineBase {
     plan_build(plan_misc_, msm_scalars_.p, n);
     tm.end();
     tm.begin("msm_exec");
-    msm_exec<F>(plan_misc_, pts, (X*)d_win_.p, ws_[5], &tm, "accum1");
-    ws_[5].tail_done.wait(st_);
+    msm_exec<F>(plan_misc_, pts, (X*)d_win_.p, ws_misc_, &tm, "accum1");
+    ws_misc_.tail_done.wait(st_);
     tm.end();
     std::vector<uint8_t> hw(MAXW * sizeof(X));
-    d2h(st_, hw.data(), d_win_.p, ws_[5].out_entries * sizeof(X));
+    d2h(st_, hw.data(), d_win_.p, ws_misc_.out_entries * sizeof(X));
     stream_sync(st_);
     tm.collect(timings);
-    HX res = n ? host_finish<HX>((const HX*)hw.data(), plan_misc_, ws_[5]) : HX::identity();
+    HX res = n ? host_finish<HX>((const HX*)hw.data(), plan_misc_, ws_misc_) : HX::identity();
     HA a = HX::to_affine(res);
     const size_t words = sizeof(A) / 4;
     uint32_t* o = (uint32_t*)out;

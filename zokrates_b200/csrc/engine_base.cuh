@@ -33,6 +33,12 @@ struct EngineBase {
   virtual void prove_begin(uint64_t pk, uint64_t r1cs, const uint64_t* z, uint32_t chain_mask, void* chain_ptrs[3],
                            uint64_t* chain_bytes) = 0;
   virtual void prove_end(uint64_t pk, uint64_t r1cs, uint8_t* partial_out) = 0;
+  virtual uint64_t prove_begin_async(uint64_t pk, uint64_t r1cs, const uint64_t* z, uint32_t chain_mask, void* chain_ptrs[3],
+                                     uint64_t* chain_bytes) = 0;
+  virtual void prove_end_async(uint64_t ticket) = 0;
+  virtual uint64_t prove_submit(uint64_t pk, uint64_t r1cs, const uint64_t* z, const uint64_t* r, const uint64_t* s) = 0;
+  virtual void prove_collect_partial(uint64_t ticket, uint8_t* partial_out) = 0;
+  virtual void prove_collect(uint64_t ticket, uint8_t* proof_out) = 0;
   virtual void finalize_prepare(uint64_t pk, const uint64_t* r, const uint64_t* s) = 0;
   virtual void finalize(uint64_t pk, const uint8_t* partials, uint32_t world, const uint64_t* r, const uint64_t* s,
                         uint8_t* proof_out) = 0;

@@ -147,8 +147,16 @@ struct Event {
   void ensure() { if (!e) ZKB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); }
   void record(Stream s) { ensure(); ZKB_CUDA(cudaEventRecord(e, s.s)); }
   void wait(Stream s) { if (e) ZKB_CUDA(cudaStreamWaitEvent(s.s, e, 0)); }
+  void sync() { if (e) ZKB_CUDA(cudaEventSynchronize(e)); }     // host waits
   void destroy() { if (e) { cudaEventDestroy(e); e = nullptr; } }
 };
+// page-locked host memory (asynchronous device -> host copies land here while the next proof's kernels run)
+inline void* host_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  ZKB_CUDA(cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault));
+  return p;
+}
+inline void host_free_pinned(void* p) { if (p) cudaFreeHost(p); }
 
 #else  // ------------------------------------------------------------------ host emulation (tests)
 
@@ -200,8 +208,15 @@ inline void stream_destroy(Stream) {}
 struct Event {
   void record(Stream) {}
   void wait(Stream) {}
+  void sync() {}
   void destroy() {}
 };
+inline void* host_alloc_pinned(size_t bytes) {
+  void* p = malloc(bytes ? bytes : 16);
+  if (!p) throw Error(ZKB_E_OOM, "malloc");
+  return p;
+}
+inline void host_free_pinned(void* p) { free(p); }
 
 #endif
 
@@ -234,6 +249,23 @@ struct DevBuf {
     count = 0;
   }
   size_t bytes() const { return count * sizeof(T); }
+};
+
+// RAII pinned host buffer
+struct HostBuf {
+  uint8_t* p = nullptr;
+  size_t count = 0;
+  HostBuf() {}
+  HostBuf(const HostBuf&) = delete;
+  HostBuf& operator=(const HostBuf&) = delete;
+  ~HostBuf() { host_free_pinned(p); }
+  void ensure(size_t n) {
+    if (n <= count) return;
+    host_free_pinned(p);
+    p = nullptr; count = 0;
+    p = (uint8_t*)host_alloc_pinned(n);
+    count = n;
+  }
 };
 
 }  // namespace zkb

@@ -75,6 +75,27 @@ def prove_partial_shared_wm(ctx, pk_h, r1cs_h, z: Optional[np.ndarray], group=No
         return ctx.prove_end(pk_h, r1cs_h)
 
 
+def submit_shared_wm(ctx, pk_h, r1cs_h, z: Optional[np.ndarray], group=None, device=None) -> int:
+    """Pipelined form of `prove_partial_shared_wm`: enqueue this rank's share of one proof (chains exchanged in the middle)
+    and return its ticket without waiting for the result — `ctx.prove_collect_partial(ticket)` follows later, typically after
+    the next proof has been submitted."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    mask = wm_chain_mask(rank, world)
+    with ctx.lock:
+        ticket, ptrs, nbytes = ctx.prove_begin_async(pk_h, r1cs_h, z, mask)
+        if mask != 7:
+            for k in range(3):
+                dist.broadcast(chain_tensor(ptrs[k], nbytes, device), src=dist.get_global_rank(group, k % world) if group else k % world,
+                               group=group)
+            if device is not None and str(device) != "cpu":
+                torch.cuda.current_stream(device).synchronize()  # the chains must be in memory before the finish step reads them
+        ctx.prove_end_async(ticket)
+    return ticket
+
+
 def prove_sharded(session, z: Optional[np.ndarray], r: int, s: int, finalize_session=None, dst: int = 0, group=None,
                   device=None) -> Optional[bytes]:
     """One proof across all ranks of `group`.  `session` holds this rank's key shard; `finalize_session`
