@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--witness", default="uniform", choices=["uniform", "bits"])
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--table-c", type=int, default=0, help="force the window width of the HBM window tables (0: cost model)")
+    ap.add_argument("--opt", action="append", default=[], metavar="ID=VALUE", help="zkb_ctx_set_option(ID, VALUE) before the key is loaded (tuning runs)")
     ap.add_argument("--pipeline", type=int, default=2, choices=[1, 2], help="proofs in flight per GPU (2: submit i+1 before collecting i)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)          # timing rule: at least three warm-up steps, in both arms
@@ -238,6 +239,9 @@ def main():
     if args.table_c:
         from zokrates_b200._lib import OPT_TABLE_C
         ctx.set_option(OPT_TABLE_C, args.table_c)
+    for kv in args.opt:
+        oid, val = kv.split("=")
+        ctx.set_option(int(oid), int(val))
     pk_h = ctx.pk_load(pk, rank, world)
     pk_bytes = len(pk)
     table_info = ctx.pk_table_info(pk_h)

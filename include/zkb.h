@@ -86,6 +86,7 @@ int32_t zkb_pk_table_info(zkb_ctx* ctx, uint64_t pk_handle, uint64_t out[8]);
 #define ZKB_OPT_Z_MODE 4        /* assignment MSMs: 0 sample z and choose (default), 1 shared-bucket table mode, 2 per-window buckets */
 #define ZKB_OPT_NTT_TILE_MIN 5  /* transforms of 2^k points and more use the shared-memory tile passes; default 10 */
 #define ZKB_OPT_NTT_MAX_S 6     /* stage bits per tile pass, 1..10; default 10 */
+#define ZKB_OPT_BITSUM_RADIX 7  /* bucket reduction by bit sums: levels of radix 2 (default) or 8 */
 int32_t zkb_ctx_set_option(zkb_ctx* ctx, int32_t option, int64_t value);
 
 /* ---- R1CS -------------------------------------------------------------------------------------

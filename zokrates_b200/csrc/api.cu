@@ -156,6 +156,7 @@ int32_t zkb_ctx_set_option(zkb_ctx* ctx, int32_t opt, int64_t value) {
       case ZKB_OPT_Z_MODE: if (value < 0 || value > 2) throw Error(ZKB_E_ARG, "ZKB_OPT_Z_MODE: 0, 1 or 2"); o.z_mode = value; break;
       case ZKB_OPT_NTT_TILE_MIN: if (value < 0 || value > 64) throw Error(ZKB_E_ARG, "ZKB_OPT_NTT_TILE_MIN"); o.ntt_tile_min = value; break;
       case ZKB_OPT_NTT_MAX_S: if (value < 1 || value > 10) throw Error(ZKB_E_ARG, "ZKB_OPT_NTT_MAX_S: 1..10"); o.ntt_max_s = value; break;
+      case ZKB_OPT_BITSUM_RADIX: if (value != 2 && value != 8) throw Error(ZKB_E_ARG, "ZKB_OPT_BITSUM_RADIX: 2 or 8"); o.bitsum_radix = value; break;
       default: throw Error(ZKB_E_ARG, "unknown option");
     }
   });

@@ -30,7 +30,7 @@ struct k_fr_convert; struct k_spmv; struct k_ntt_dif; struct k_ntt_dit; struct k
 struct k_ntt_table; struct k_qap_pointwise; struct k_msm_digits; struct k_msm_scatter; struct k_msm_accum1;
 struct k_msm_accum2; struct k_msm_bitsum; struct k_pk_convert; struct k_final_a; struct k_final_b;
 struct k_final_c; struct k_final_d; struct k_point_out; struct k_field_op; struct k_setup_scalars; struct k_fixed_base;
-struct k_to_affine; struct k_copy; struct k_msm_table; struct k_ntt_dif_tile; struct k_ntt_dit_tile; struct k_witness_level;
+struct k_to_affine; struct k_copy; struct k_msm_view; struct k_msm_table; struct k_ntt_dif_tile; struct k_ntt_dit_tile; struct k_witness_level;
 
 // ---------------------------------------------------------------------------------------------
 // stage timer: CUDA events on the engine stream (no-op in the host emulation)
@@ -174,6 +174,74 @@ inline void exclusive_scan(Stream st, const uint32_t* counts, uint32_t* offsets,
 #endif
 }
 
+// ---- MSM views by stable compaction of the sorted list (msm.cuh: "views") -----------------------------------------
+static constexpr int VIEW_BLOCK = 256, VIEW_ITERS = 8, VIEW_TILE = VIEW_BLOCK * VIEW_ITERS, VIEW_GROUPS = VIEW_TILE / 32;
+#if !defined(ZKB_EMU)
+// phase 1: kept entries of view 1 and view 2 per tile of 2048 sorted positions
+static __global__ void __launch_bounds__(VIEW_BLOCK) zkb_view_count(MsmShape sh, const uint8_t* skip, const uint32_t* sorted0,
+                                                                    const uint32_t* offsets0, uint32_t NB, uint32_t* tile_cnt,
+                                                                    uint32_t ntiles) {
+  __shared__ uint32_t cnt[2];
+  if (threadIdx.x < 2) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t M = offsets0[NB];
+  uint32_t c1 = 0, c2 = 0;
+#pragma unroll
+  for (int it = 0; it < VIEW_ITERS; it++) {
+    const uint32_t p = blockIdx.x * VIEW_TILE + it * VIEW_BLOCK + threadIdx.x;
+    if (p < M) {
+      const uint32_t e = sorted0[p];
+      c1 += msm_view_keep(sh, skip, e, 1);
+      c2 += msm_view_keep(sh, skip, e, 2);
+    }
+  }
+  for (int off = 16; off; off >>= 1) { c1 += __shfl_down_sync(0xffffffffu, c1, off); c2 += __shfl_down_sync(0xffffffffu, c2, off); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&cnt[0], c1); atomicAdd(&cnt[1], c2); }
+  __syncthreads();
+  if (threadIdx.x < 2) tile_cnt[threadIdx.x * ntiles + blockIdx.x] = cnt[threadIdx.x];
+}
+// phase 3: write the kept entries at tile offset + rank inside the tile; keep (exclusive count, keep-mask) per 32 positions
+static __global__ void __launch_bounds__(VIEW_BLOCK) zkb_view_apply(MsmShape sh, const uint8_t* skip, const uint32_t* sorted0,
+                                                                    const uint32_t* offsets0, uint32_t NB, uint32_t nv,
+                                                                    const uint32_t* tile_off, uint32_t ntiles, uint32_t* sorted_v,
+                                                                    size_t total, uint32_t* pre32, uint32_t* mask32, uint32_t ngroups) {
+  __shared__ uint32_t gcnt[2][VIEW_GROUPS];
+  const uint32_t M = offsets0[NB];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t e[VIEW_ITERS], m[2][VIEW_ITERS];
+#pragma unroll
+  for (int it = 0; it < VIEW_ITERS; it++) {
+    const uint32_t p = blockIdx.x * VIEW_TILE + it * VIEW_BLOCK + threadIdx.x;
+    const bool valid = p < M;
+    e[it] = valid ? sorted0[p] : 0;
+    const bool f1 = valid && msm_view_keep(sh, skip, e[it], 1), f2 = valid && msm_view_keep(sh, skip, e[it], 2);
+    m[0][it] = __ballot_sync(0xffffffffu, f1);
+    m[1][it] = __ballot_sync(0xffffffffu, f2);
+    if (lane == 0) { gcnt[0][it * 8 + warp] = __popc(m[0][it]); gcnt[1][it * 8 + warp] = __popc(m[1][it]); }
+  }
+  __syncthreads();
+  if (warp < 2) {  // exclusive scan of the 64 group counts of view `warp`: two groups per lane
+    const uint32_t a = gcnt[warp][2 * lane], b = gcnt[warp][2 * lane + 1];
+    uint32_t incl = a + b;
+    for (int off = 1; off < 32; off <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= (uint32_t)off) incl += y; }
+    const uint32_t excl = incl - (a + b);
+    gcnt[warp][2 * lane] = excl;
+    gcnt[warp][2 * lane + 1] = excl + a;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < VIEW_ITERS; it++) {
+    const uint32_t p = blockIdx.x * VIEW_TILE + it * VIEW_BLOCK + threadIdx.x;
+    for (uint32_t v = 0; v < nv; v++) {
+      const uint32_t base = tile_off[(size_t)v * (ntiles + 1) + blockIdx.x] + gcnt[v][it * 8 + warp];
+      const uint32_t mk = m[v][it];
+      if (lane == 0 && p < M) { pre32[(size_t)v * ngroups + (p >> 5)] = base; mask32[(size_t)v * ngroups + (p >> 5)] = mk; }
+      if ((mk >> lane) & 1u) sorted_v[(size_t)v * total + base + __popc(mk & ((1u << lane) - 1u))] = e[it];
+    }
+  }
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------
 struct MsmPlan {
   MsmShape sh{0, 0, 0, 0, 0};
@@ -181,7 +249,8 @@ struct MsmPlan {
   uint32_t T1 = 32, T2 = 32;
   uint32_t nt1 = 0;  // level-1 chunks
   uint32_t nviews = 1;
-  DevBuf<uint32_t> digits, counts, offsets, cursor, sorted, scan_tmp;
+  DevBuf<uint32_t> digits, ranks, counts, offsets, sorted, scan_tmp;
+  DevBuf<uint32_t> view_tile_cnt, view_tile_off, view_pre32, view_mask32;   // views by compaction (build_views)
 };
 
 inline uint32_t msm_pick_c(uint64_t n, int fr_bits) {
@@ -508,9 +577,9 @@ class Engine : public EngineBase {
     Stream tail;          // high-priority side stream for accum2 / bit sums
     Event acc_done, tail_done;
     bool has_stream = false;
-    // filled by msm_tail: the bit-sum reduction ran `tree_lvls` levels and left `tree_cnt` block totals per window
-    uint32_t tree_cnt = 1, tree_lvls = 0;
-    size_t out_entries = 0;   // XYZZ entries of the result slot the host has to read: (1 + 3 * tree_lvls) * W * tree_cnt
+    // filled by msm_tail: the bit-sum reduction consumed `tree_bits` index bits and left `tree_cnt` block totals per window
+    uint32_t tree_cnt = 1, tree_bits = 0;
+    size_t out_entries = 0;   // XYZZ entries of the result slot the host has to read: (1 + tree_bits) * W * tree_cnt
     void destroy() { if (has_stream) { stream_destroy(tail); has_stream = false; } acc_done.destroy(); tail_done.destroy(); }
   };
   struct ProofSlot {
@@ -687,18 +756,60 @@ class Engine : public EngineBase {
     pl.T2 = 8;   // short chunks at the partial levels: fewer dependent additions per level
     pl.nt1 = (uint32_t)((total + pl.T1 - 1) / pl.T1);
     const uint32_t NB = pl.nbuckets;
-    pl.digits.ensure(total); pl.sorted.ensure(total * nviews);
-    pl.counts.ensure((size_t)NB * nviews); pl.cursor.ensure((size_t)NB * nviews); pl.offsets.ensure((size_t)(NB + 1) * nviews);
-    dev_zero(st_, pl.counts.p, (size_t)NB * nviews * 4);
-    dev_zero(st_, pl.cursor.p, (size_t)NB * nviews * 4);
+    if (nviews > 3) throw Error(ZKB_E_INTERNAL, "at most two filtered views");
+    pl.digits.ensure(total); pl.ranks.ensure(total); pl.sorted.ensure(total * nviews);
+    pl.counts.ensure(NB); pl.offsets.ensure((size_t)(NB + 1) * nviews);
+    dev_zero(st_, pl.counts.p, (size_t)NB * 4);
     MsmShape sh = pl.sh;
     const uint32_t* sc = (const uint32_t*)scalars;
-    uint32_t* dg = pl.digits.p; uint32_t* cn = pl.counts.p; uint32_t* of = pl.offsets.p; uint32_t* cu = pl.cursor.p;
+    uint32_t* dg = pl.digits.p; uint32_t* rk = pl.ranks.p; uint32_t* cn = pl.counts.p; uint32_t* of = pl.offsets.p;
     uint32_t* so = pl.sorted.p;
-    launch<k_msm_digits>(st_, n, ZKB_LAMBDA(size_t t) { msm_digits_body(sh, nviews, skip, sc, dg, cn, (uint32_t)t); });
-    pl.scan_tmp.ensure(2 * (NB / 2048 + 4));
-    for (uint32_t v = 0; v < nviews; v++) exclusive_scan(st_, cn + (size_t)v * NB, of + (size_t)v * (NB + 1), NB, pl.scan_tmp.p);
-    launch<k_msm_scatter>(st_, total, ZKB_LAMBDA(size_t t) { msm_scatter_body(sh, nviews, skip, dg, of, cu, so, t); });
+    launch<k_msm_digits>(st_, n, ZKB_LAMBDA(size_t t) { msm_digits_body(sh, sc, dg, rk, cn, (uint32_t)t); });
+    const uint32_t ntiles = (uint32_t)((total + VIEW_TILE - 1) / VIEW_TILE);
+    pl.scan_tmp.ensure(2 * ((size_t)(NB > ntiles ? NB : ntiles) / 2048 + 4));
+    exclusive_scan(st_, cn, of, NB, pl.scan_tmp.p);
+    launch<k_msm_scatter>(st_, total, ZKB_LAMBDA(size_t t) { msm_scatter_body(sh, dg, rk, of, so, t); });
+    if (nviews > 1) build_views(pl, skip, total, ntiles);
+  }
+
+  // views 1.. = stable compaction of the sorted list of view 0 (kernels above; host loop in the emulation)
+  void build_views(MsmPlan& pl, const uint8_t* skip, uint64_t total, uint32_t ntiles) {
+    const uint32_t NB = pl.nbuckets, nv = pl.nviews - 1;
+    const MsmShape sh = pl.sh;
+    const uint32_t* of0 = pl.offsets.p;
+    const uint32_t* so0 = pl.sorted.p;
+    uint32_t* sov = pl.sorted.p + total;
+#if !defined(ZKB_EMU)
+    const uint32_t ngroups = (uint32_t)((total + 31) / 32);
+    pl.view_tile_cnt.ensure((size_t)2 * ntiles); pl.view_tile_off.ensure((size_t)2 * (ntiles + 1));
+    pl.view_pre32.ensure((size_t)2 * ngroups); pl.view_mask32.ensure((size_t)2 * ngroups);
+    launch_counter() += 2;
+    zkb_view_count<<<ntiles, VIEW_BLOCK, 0, st_.s>>>(sh, skip, so0, of0, NB, pl.view_tile_cnt.p, ntiles);
+    ZKB_CUDA(cudaGetLastError());
+    for (uint32_t v = 0; v < nv; v++)
+      exclusive_scan(st_, pl.view_tile_cnt.p + (size_t)v * ntiles, pl.view_tile_off.p + (size_t)v * (ntiles + 1), ntiles, pl.scan_tmp.p);
+    zkb_view_apply<<<ntiles, VIEW_BLOCK, 0, st_.s>>>(sh, skip, so0, of0, NB, nv, pl.view_tile_off.p, ntiles, sov, (size_t)total,
+                                                     pl.view_pre32.p, pl.view_mask32.p, ngroups);
+    ZKB_CUDA(cudaGetLastError());
+    for (uint32_t v = 0; v < nv; v++) {
+      const uint32_t* pre = pl.view_pre32.p + (size_t)v * ngroups; const uint32_t* msk = pl.view_mask32.p + (size_t)v * ngroups;
+      const uint32_t* tot = pl.view_tile_off.p + (size_t)v * (ntiles + 1) + ntiles;
+      uint32_t* ofv = pl.offsets.p + (size_t)(v + 1) * (NB + 1);
+      launch<k_msm_view>(st_, (size_t)NB + 1, ZKB_LAMBDA(size_t t) { msm_view_offsets_body(NB, of0, pre, msk, tot, ofv, (uint32_t)t); });
+    }
+#else
+    (void)ntiles;
+    const uint32_t M = of0[NB];
+    for (uint32_t v = 0; v < nv; v++) {
+      uint32_t* ofv = pl.offsets.p + (size_t)(v + 1) * (NB + 1);
+      uint32_t* out = sov + (size_t)v * total;
+      uint32_t kept = 0, b = 0;
+      for (uint32_t p = 0; p <= M; p++) {
+        while (b <= NB && of0[b] == p) ofv[b++] = kept;
+        if (p < M && msm_view_keep(sh, skip, so0[p], v + 1)) out[kept++] = so0[p];
+      }
+    }
+#endif
   }
 
   MsmWs ws_misc_;       // standalone zkb_msm_g1 / g2
@@ -770,30 +881,43 @@ class Engine : public EngineBase {
       L = 2 * nt;
       cur ^= 1;
     }
-    // bucket reduction by bit sums (msm.cuh::msm_bitsum_body): one launch per 3 index bits, 7 dependent additions each
-    const size_t first = (size_t)W * (B >> 3);
-    ws.tree[0].ensure((first + 1) * sizeof(X)); ws.tree[1].ensure((first / 8 + 1) * sizeof(X));
-    ws.tree[2].ensure((3 * first + 1) * sizeof(X)); ws.tree[3].ensure((3 * first + 1) * sizeof(X));
+    // bucket reduction by bit sums (msm.cuh::msm_bitsum2_body / msm_bitsum_body): one launch per level, 1 (radix 2, default)
+    // or 7 (radix 8) dependent additions each
+    const uint32_t rbits = opts.bitsum_radix == 8 ? 3u : 1u;
+    const size_t half = ((size_t)W * B) >> 1;   // largest level output: A' <= W B / 2 entries, pending <= W B / 2 entries
+    if (rbits == 3) {
+      const size_t first = (size_t)W * (B >> 3);
+      ws.tree[0].ensure((first + 1) * sizeof(X)); ws.tree[1].ensure((first / 8 + 1) * sizeof(X));
+      ws.tree[2].ensure((3 * first + 1) * sizeof(X)); ws.tree[3].ensure((3 * first + 1) * sizeof(X));
+    } else {
+      ws.tree[0].ensure((half + 1) * sizeof(X)); ws.tree[1].ensure((half / 2 + 1) * sizeof(X));
+      ws.tree[2].ensure((half + 1) * sizeof(X)); ws.tree[3].ensure((half + 1) * sizeof(X));
+    }
     const X* inA = buckets; const X* inP = nullptr;
-    uint32_t cnt = B, lvl = 0;
+    uint32_t cnt = B, lvl = 0, nbits = 0;
     // a G2 addition costs 1.3 us on a host core against 0.45 us in G1, and the G2 tail is never the last to finish:
     // run it further down on the GPU
     const size_t host_nodes = sizeof(F) > sizeof(Fq) ? HOST_TREE_NODES / 8 : HOST_TREE_NODES;
-    while (cnt >= 8 && (size_t)W * cnt > host_nodes) {
+    while (cnt >= (1u << rbits) && (size_t)W * cnt > host_nodes) {
       X* oA = (X*)ws.tree[lvl & 1].p; X* oP = (X*)ws.tree[2 + (lvl & 1)].p;
       const X* iA = inA; const X* iP = inP;
-      const uint32_t ci = cnt, np = 3 * lvl;
-      const size_t threads = (size_t)(4 + np) * W * (cnt >> 3);
-      launch<k_msm_bitsum>(ts, threads, ZKB_LAMBDA(size_t t) { msm_bitsum_body<F>(W, ci, np, iA, iP, oA, oP, (uint32_t)t); });
-      inA = oA; inP = oP; cnt >>= 3; lvl++;
+      const uint32_t ci = cnt, np = nbits;
+      if (rbits == 3) {
+        const size_t threads = (size_t)(4 + np) * W * (cnt >> 3);
+        launch<k_msm_bitsum>(ts, threads, ZKB_LAMBDA(size_t t) { msm_bitsum_body<F>(W, ci, np, iA, iP, oA, oP, (uint32_t)t); });
+      } else {
+        const size_t threads = (size_t)(2 + np) * W * (cnt >> 1);
+        launch<k_msm_bitsum, 64>(ts, threads, ZKB_LAMBDA(size_t t) { msm_bitsum2_body<F>(W, ci, np, iA, iP, oA, oP, (uint32_t)t); });
+      }
+      inA = oA; inP = oP; cnt >>= rbits; lvl++; nbits += rbits;
     }
-    // result slot: [A : W*cnt][pending 0 : W*cnt] ... [pending 3*lvl-1 : W*cnt]; the host finishes (host_finish)
-    ws.tree_cnt = cnt; ws.tree_lvls = lvl;
+    // result slot: [A : W*cnt][pending 0 : W*cnt] ... [pending nbits-1 : W*cnt]; the host finishes (host_finish)
+    ws.tree_cnt = cnt; ws.tree_bits = nbits;
     const size_t nodes = (size_t)W * cnt;
-    ws.out_entries = nodes * (1 + 3 * (size_t)lvl);
+    ws.out_entries = nodes * (1 + (size_t)nbits);
     if (ws.out_entries > MAXW) throw Error(ZKB_E_INTERNAL, "msm result slot overflow");
     d2d(ts, win_out, inA, nodes * sizeof(X));
-    if (lvl) d2d(ts, win_out + nodes, inP, nodes * 3 * lvl * sizeof(X));
+    if (nbits) d2d(ts, win_out + nodes, inP, nodes * nbits * sizeof(X));
     if (tm && tail_name) tm->end_on(ts, span);
     ws.tail_done.record(ts);
   }
@@ -806,12 +930,12 @@ class Engine : public EngineBase {
   }
 
   // Host finish of one MSM.  Per window: total = sum_k A_k, hi = sum_k k A_k (running sums), S_bit = sum_k P_bit[k];
-  //   sum_j (j + 1) B_j = total + sum_bit 2^bit S_bit + 2^(3 L) hi    (Horner from the top bit),
+  //   sum_j (j + 1) B_j = total + sum_bit 2^bit S_bit + 2^nbits hi    (Horner from the top bit),
   // then result = sum_w 2^(c w) (window sum).  A few hundred point additions on a host core.
   static constexpr size_t HOST_TREE_NODES = 32;
   template <class HX>
   static HX host_finish(const HX* slot, const MsmPlan& pl, const MsmWs& ws) {
-    const uint32_t W = pl.sh.pre ? 1 : pl.sh.W, cnt = ws.tree_cnt, L = ws.tree_lvls, c = pl.sh.c;
+    const uint32_t W = pl.sh.pre ? 1 : pl.sh.W, cnt = ws.tree_cnt, nbits = ws.tree_bits, c = pl.sh.c;
     const size_t nodes = (size_t)W * cnt;
     const HX* A = slot;
     auto window_sum = [&](uint32_t w) {
@@ -820,7 +944,7 @@ class Engine : public EngineBase {
         run = HX::add(run, A[(size_t)w * cnt + k]);
         if (k > 0) hi = HX::add(hi, run);
       }
-      for (uint32_t bit = 3 * L; bit-- > 0;) {
+      for (uint32_t bit = nbits; bit-- > 0;) {
         const HX* P = slot + nodes * (1 + (size_t)bit) + (size_t)w * cnt;
         HX sb = HX::identity();
         for (uint32_t k = 0; k < cnt; k++) sb = HX::add(sb, P[k]);

@@ -15,6 +15,7 @@ struct Options {
   int64_t z_mode = 0;         // ZKB_OPT_Z_MODE: 0 sample the assignment, 1 always the shared-bucket table mode, 2 always per-window buckets
   int64_t ntt_tile_min = 10;  // ZKB_OPT_NTT_TILE_MIN: transforms of 2^k points and more use the shared-memory tile passes
   int64_t ntt_max_s = 10;     // ZKB_OPT_NTT_MAX_S: stage bits per tile pass
+  int64_t bitsum_radix = 2;   // ZKB_OPT_BITSUM_RADIX: bucket-reduction levels of radix 2 (1 dependent addition per launch) or 8 (7)
 };
 
 struct EngineBase {

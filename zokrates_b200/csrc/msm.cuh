@@ -50,18 +50,14 @@ ZKB_HD uint32_t scalar_bits(const uint32_t* s, uint32_t lo, uint32_t cnt) {
 }
 
 // ---- digits + histogram: one thread per scalar -------------------------------------------------
-// digits[w * n + i] = (|d| - 1) | sign, or MSM_NONE when d == 0.
-// Views: one digit decomposition can feed several sorted lists that differ in which points they skip
-// (view 0 keeps everything; view v > 0 drops pair i when bit (v-1) of skip[i] is set — the points that are
-// the point at infinity in that query vector, which ark's add_assign_mixed also treats as a no-op).
-ZKB_HDN inline void msm_digits_body(MsmShape sh, uint32_t nviews, const uint8_t* skip, const uint32_t* scalars /* n x 8, canonical */,
-                                    uint32_t* digits, uint32_t* counts /* nviews x W*B */, uint32_t i) {
+// digits[w * n + i] = (|d| - 1) | sign, or MSM_NONE when d == 0;  ranks[w * n + i] = arrival order of the entry inside its
+// bucket (the value the histogram atomic returned), so the scatter needs no second atomic.
+ZKB_HDN inline void msm_digits_body(MsmShape sh, const uint32_t* scalars /* n x 8, canonical */, uint32_t* digits, uint32_t* ranks,
+                                    uint32_t* counts /* W*B (or B with tables) */, uint32_t i) {
   if (i >= sh.n) return;
   uint32_t s[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) s[k] = scalars[(size_t)i * 8 + k];
-  const uint32_t sk = skip ? skip[i] : 0;
-  const uint32_t NB = msm_nbuckets(sh);
   uint32_t carry = 0;
   const uint32_t full = 1u << sh.c, half = sh.B;
   for (uint32_t w = 0; w < sh.W; w++) {
@@ -83,33 +79,49 @@ ZKB_HDN inline void msm_digits_body(MsmShape sh, uint32_t nviews, const uint8_t*
     digits[(size_t)w * sh.n + i] = code;
     if (code != MSM_NONE) {
       const uint32_t key = (sh.pre ? 0u : w * sh.B) + (code & ~MSM_NEG);
-      zkb_atomic_add(&counts[key], 1);
-      for (uint32_t v = 1; v < nviews; v++)
-        if (!((sk >> (v - 1)) & 1u)) zkb_atomic_add(&counts[(size_t)v * NB + key], 1);
+      ranks[(size_t)w * sh.n + i] = zkb_atomic_add(&counts[key], 1);
     }
   }
 }
 
 // ---- scatter: one thread per (window, scalar) --------------------------------------------------
-// offsets: nviews x (NB+1), cursor: nviews x NB, sorted: nviews x (n*W)
-ZKB_HDN inline void msm_scatter_body(MsmShape sh, uint32_t nviews, const uint8_t* skip, const uint32_t* digits,
-                                     const uint32_t* offsets, uint32_t* cursor, uint32_t* sorted, size_t t) {
+// sorted[offsets[key] + rank] = point index | sign      (counting sort; the order inside a bucket is irrelevant: sums)
+ZKB_HDN inline void msm_scatter_body(MsmShape sh, const uint32_t* digits, const uint32_t* ranks, const uint32_t* offsets,
+                                     uint32_t* sorted, size_t t) {
   const size_t total = (size_t)sh.n * sh.W;
   if (t >= total) return;
   uint32_t code = digits[t];
   if (code == MSM_NONE) return;
-  const uint32_t NB = msm_nbuckets(sh);
   uint32_t w = (uint32_t)(t / sh.n), i = (uint32_t)(t % sh.n);
   uint32_t key = (sh.pre ? 0u : w * sh.B) + (code & ~MSM_NEG);
-  const uint32_t sk = skip ? skip[i] : 0;
   const uint32_t val = (sh.pre ? w * sh.n + i : i) | (code & MSM_NEG);
-  uint32_t pos = zkb_atomic_add(&cursor[key], 1);
-  sorted[offsets[key] + pos] = val;
-  for (uint32_t v = 1; v < nviews; v++)
-    if (!((sk >> (v - 1)) & 1u)) {
-      uint32_t p2 = zkb_atomic_add(&cursor[(size_t)v * NB + key], 1);
-      sorted[(size_t)v * total + offsets[(size_t)v * (NB + 1) + key] + p2] = val;
-    }
+  sorted[offsets[key] + ranks[t]] = val;
+}
+
+// ---- views: filtered copies of the sorted list ----------------------------------------------------
+// View v > 0 drops the pairs whose point is the point at infinity in that query vector (bit v-1 of skip[i]; ark's
+// add_assign_mixed treats them as a no-op too).  A view is a STABLE COMPACTION of the sorted list of view 0 — a streaming
+// pass with ballots and a tile scan instead of a second and third round of histogram / cursor atomics (round 1: the
+// three-view plan cost 2.6 ms per proof, most of it atomics).  Per group of 32 consecutive sorted positions the pass keeps
+// the keep-mask and the exclusive count before the group, from which the bucket offsets of the view follow:
+//   offsets_v[b] = pre32[g] + popc(mask32[g] & lanes below p),  p = offsets_0[b], g = p / 32.
+ZKB_HD uint32_t msm_view_keep(const MsmShape& sh, const uint8_t* skip, uint32_t entry, uint32_t v) {
+  const uint32_t idx = entry & ~MSM_NEG;
+  const uint32_t i = sh.pre ? idx % sh.n : idx;
+  return !((skip[i] >> (v - 1)) & 1u);
+}
+ZKB_HDN inline void msm_view_offsets_body(uint32_t NB, const uint32_t* offsets0, const uint32_t* pre32, const uint32_t* mask32,
+                                          const uint32_t* total_v, uint32_t* offsets_v, uint32_t b) {
+  if (b > NB) return;
+  const uint32_t M = offsets0[NB], p = offsets0[b];
+  if (p >= M) { offsets_v[b] = *total_v; return; }
+  const uint32_t g = p >> 5, lane = p & 31u;
+  const uint32_t below = mask32[g] & ((1u << lane) - 1u);
+#if defined(__CUDA_ARCH__)
+  offsets_v[b] = pre32[g] + __popc(below);
+#else
+  offsets_v[b] = pre32[g] + (uint32_t)__builtin_popcount(below);
+#endif
 }
 
 // ---- level-1 accumulate: affine points, keys implied by the offsets array -----------------------
@@ -293,6 +305,28 @@ ZKB_HDN inline void msm_bitsum_body(uint32_t W, uint32_t cnt_in, uint32_t npend,
   else if (role < 4) dst = outP + (size_t)(npend + role - 1) * per_role;
   else dst = outP + (size_t)(role - 4) * per_role;
   dst[node] = sum;
+}
+
+// ---- radix-2 level of the same scheme: cnt_in -> cnt_in / 2, ONE dependent addition per level ------------------------
+// role 0        : A'[k]   = A[2k] + A[2k+1]
+// role 1+r      : P_r'[k] = P_r[2k] + P_r[2k+1]        (r < npend: plain halving of the older bit-sum arrays)
+// role 1+npend  : P_new[k] = A[2k+1]                   (the entries whose index bit `level` is set: a copy, no arithmetic)
+// Pending array r holds index bit r.  Against the radix-8 level this is less work (4 instead of 9 additions per 8 entries
+// for the new bits) and, above all, a dependent chain of 1 instead of 7 additions per launch: the upper levels are pure
+// latency (a G2 addition is ~28 us on one thread), so the tail of an MSM shrinks by the ratio of the chain lengths.
+template <class F>
+ZKB_HDN inline void msm_bitsum2_body(uint32_t W, uint32_t cnt_in, uint32_t npend, const XYZZ<F>* inA, const XYZZ<F>* inP,
+                                     XYZZ<F>* outA, XYZZ<F>* outP, uint32_t t) {
+  const uint32_t cnt_out = cnt_in >> 1;
+  const uint32_t per_role = W * cnt_out;
+  const uint32_t role = t / per_role, node = t % per_role;
+  if (role >= 2 + npend) return;
+  const uint32_t w = node / cnt_out, k = node % cnt_out;
+  const bool from_a = role == 0 || role == 1 + npend;
+  const XYZZ<F>* src = (from_a ? inA : inP + (size_t)(role - 1) * W * cnt_in) + (size_t)w * cnt_in + ((size_t)k << 1);
+  if (role == 0) outA[node] = XYZZ<F>::add(src[0], src[1]);
+  else if (role == 1 + npend) outP[(size_t)npend * per_role + node] = src[1];
+  else outP[(size_t)(role - 1) * per_role + node] = XYZZ<F>::add(src[0], src[1]);
 }
 
 }  // namespace zkb
