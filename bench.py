@@ -378,6 +378,7 @@ def main():
         mads = MADS_PER_MUL[args.curve]
         imad_peak = ctx.peak_probe(0, 40000)             # 32x32+64 multiply-adds per second, dependent-free IMAD.WIDE.U32 chains
         mul_probe = ctx.peak_probe(1, 4000)              # this repo's own register-resident Montgomery multiplication (secondary)
+        carry_peak = ctx.peak_probe(2, 10000)            # the same wide MADs carry-chained (IMAD.WIDE.U32.X), as a multiplier issues them
         g1_bytes = 64 if cid == 0 else 96
         alg_bytes = n_pairs * (32.0 + g1_bytes)          # 32 B scalar + one affine point per pair
         alg_muls = n_pairs * 16 * 10.0                   # canonical: W = 16 windows x 10 Fq-mul per mixed add
@@ -400,6 +401,10 @@ def main():
                                     "bytes-for-multiplications trade (fewer mixed additions per scalar, one bucket set); not binding (about 10 % of HBM peak)",
                     "hbm": {"achieved": alg_bytes / (acc_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": alg_bytes / (acc_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},
+                    "carry_chain": {"peak": carry_peak / mads, "unit": "Fq-mul/s", "frac": achieved / (carry_peak / mads), "mad_per_s": carry_peak,
+                                    "note": "zkb_peak_probe kind 2: rows of carry-chained wide MADs (1 IMAD.WIDE.U32 + 7 IMAD.WIDE.U32.X); the .X form "
+                                            "occupies the fmaheavy pipe longer than the carry-free form of kind 0, and ncu names that pipe as the "
+                                            "binding unit of the kernel (sm__pipe_fmaheavy_cycles_active 87.6 %, profiles/r02_ncu_accum1_g2.md)"},
                     "mul_probe": {"peak": mul_probe, "unit": "Fq-mul/s", "frac": achieved / mul_probe,
                                   "note": "this repo's own Fp::mul in a register-resident loop — self-referential, secondary"}}
 

@@ -87,6 +87,11 @@ int32_t zkb_pk_table_info(zkb_ctx* ctx, uint64_t pk_handle, uint64_t out[8]);
 #define ZKB_OPT_NTT_TILE_MIN 5  /* transforms of 2^k points and more use the shared-memory tile passes; default 10 */
 #define ZKB_OPT_NTT_MAX_S 6     /* stage bits per tile pass, 1..10; default 10 */
 #define ZKB_OPT_BITSUM_RADIX 7  /* bucket reduction by bit sums: levels of radix 2 (default) or 8 */
+#define ZKB_OPT_NTT_KERNEL 9    /* tile pass of the NTT: 2 (default) four-step twiddles + cp.async tile load, 1 the round-1 pass */
+#define ZKB_OPT_PK_CACHE 8      /* 1 (default): zkb_pk_load of bytes that are already resident returns a handle onto the same key
+                                 * (content fingerprint), and the last key released by zkb_pk_free stays resident until another
+                                 * key is loaded — the per-call pk_load / prove / pk_free of the static trait method then builds
+                                 * the window tables once; 0: every load builds, every free releases */
 int32_t zkb_ctx_set_option(zkb_ctx* ctx, int32_t option, int64_t value);
 
 /* ---- R1CS -------------------------------------------------------------------------------------
@@ -177,6 +182,32 @@ int32_t zkb_r1cs_check(zkb_ctx* ctx, uint64_t r1cs_handle, const uint64_t* z, ui
 int32_t zkb_witness_eval(zkb_ctx* ctx, uint64_t r1cs_handle, uint64_t* z_inout, uint32_t n_levels,
                          const uint32_t* level_ptr, const uint32_t* rows, const uint32_t* out_var,
                          uint64_t* first_unsatisfied);
+
+/* ---- compiled programs: the native front door --------------------------------
+ * zkb_prog_load: `out_bytes` is the compiled-program file `zokrates compile` writes and `generate-proof -i out` /
+ *   `compute-witness -i out` read (header + serde_cbor sections, zokrates_ast/src/ir/serialize.rs:124-189,295-391).  The
+ *   library parses it natively, synthesises the R1CS in ark variable order (`Computation::generate_constraints`,
+ *   zokrates_ark/src/lib.rs:41-130) and keeps it resident: info[7] is an ordinary R1CS handle (owned by the program) for
+ *   zkb_groth16_prove* / zkb_groth16_setup.  It also schedules the statements by dependency level.
+ * zkb_prog_info: out[0] constraints, [1] instance variables incl. one, [2] witness variables, [3] arguments, [4] return
+ *   values, [5] directives, [6] levels, [7] R1CS handle, [8] variables only directives touch, [9] directives whose solver has
+ *   no device path (Zir functions, embed gadgets), [10] public arguments, [11] 1 if the statements can be scheduled.
+ * zkb_prog_compute_witness: `Interpreter::execute` on the device (zokrates_interpreter/src/lib.rs:40-138): constraints assign
+ *   or check, directives run the solver kernels (ConditionEq, Bits incl. the out-of-range path with flag 1 =
+ *   `try_out_of_range`, Div, Xor, Or, ShaAndXorAndXorAnd, ShaCh, EuclideanDiv; :140-165,249-307).  inputs: n_inputs canonical
+ *   field elements (32 bytes each), one per argument.  witness_out (may be NULL) receives the witness FILE bytes
+ *   (`Witness::write`, zokrates_ast/src/ir/witness.rs:44-53); *witness_len its length.  The assignment stays resident for
+ *   zkb_groth16_prove_resident.  ZKB_E_UNSAT + *first_unsatisfied on a violated constraint; ZKB_E_ARG "WrongInputCount".
+ * zkb_prog_set_witness: `Witness::read` (:55-71) of a witness file into the resident assignment (ark column order).
+ * zkb_prog_public_inputs: public arguments in declaration order, then ~out_0.. (ir/mod.rs:278-288) of the current
+ *   assignment, canonical, 32 bytes each; out may be NULL to query *count. */
+int32_t zkb_prog_load(zkb_ctx* ctx, const uint8_t* out_bytes, size_t len, uint64_t* prog_handle);
+int32_t zkb_prog_info(zkb_ctx* ctx, uint64_t prog_handle, uint64_t out[12]);
+int32_t zkb_prog_free(zkb_ctx* ctx, uint64_t prog_handle);
+int32_t zkb_prog_compute_witness(zkb_ctx* ctx, uint64_t prog_handle, const uint64_t* inputs, uint64_t n_inputs, uint32_t flags,
+                                 uint8_t* witness_out, size_t witness_cap, size_t* witness_len, uint64_t* first_unsatisfied);
+int32_t zkb_prog_set_witness(zkb_ctx* ctx, uint64_t prog_handle, const uint8_t* witness_bytes, size_t len);
+int32_t zkb_prog_public_inputs(zkb_ctx* ctx, uint64_t prog_handle, uint64_t* out, uint64_t cap, uint64_t* count);
 
 /* ---- building blocks (micro-benchmarks and parity tests; BASELINE.json config 5) ---------------
  * points: ark uncompressed affine encoding (x | y, canonical LE, infinity flag 0x40 in the last

@@ -5,8 +5,7 @@ host add), NTT replicated per GPU.  Launch with torchrun, one rank per GPU:
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/microbench_multi.py 20 22
 
 Times are wall clock around the call, barrier + synchronize on both sides, max over ranks; points are the h_query of a GPU-made
-proving key (distinct non-infinity points).  Prints one JSON line per size on rank 0.  (Not yet run on hardware in round 1: the
-GPU budget went to the prover itself; the same path is covered on gloo by tests/test_multi_gpu_gloo.py::test_sharded_msm_gloo.)
+proving key (distinct non-infinity points).  Prints one JSON line per size on rank 0.  (The same path is covered on gloo by tests/test_multi_gpu_gloo.py::test_sharded_msm_gloo.)
 """
 import json
 import os
@@ -31,7 +30,7 @@ def main():
     dev = torch.device("cuda", local)
     sizes = [int(a) for a in sys.argv[1:]] or [18, 20]
     ctx = Context(0, local, Library())
-    lg_max = max(sizes)
+    lg_max = min(max(sizes), int(os.environ.get("ZKB_POINTS_MAX_LOG", "24")))   # larger sizes tile this point set (timing only)
     r1cs, z = synthetic.make_layered(ctx, "bn128", (1 << lg_max) - 2)
     h = ctx.r1cs_load(r1cs.num_constraints, r1cs.num_instance, r1cs.num_witness, r1cs.matrices())
     pk = ctx.setup(h, [11, 22, 33, 44, 5555, 3, 7])
@@ -48,7 +47,8 @@ def main():
 
     for lg in sizes:
         n = (1 << lg) - 1
-        pts = hq[:n * 64].tobytes()
+        reps = -(-n // ((1 << lg_max) - 1))
+        pts = (np.tile(hq, reps)[:n * 64] if reps > 1 else hq[:n * 64]).tobytes()
         sc = rs.randint(0, 1 << 62, size=(n, 4)).astype(np.uint64)
         sc[:, 3] &= np.uint64((1 << 60) - 1)
         best = None
@@ -67,7 +67,7 @@ def main():
         ntt_ms = ctx.timings()["ntt"]
         if rank == 0:
             ms = float(tt.item()) * 1e3
-            print(json.dumps({"log_n": lg, "n_gpus": world, "msm_g1_ms_incl_h2d": ms, "msm_fq_mul_per_s": n * 16 * 10 / (ms * 1e-3),
+            print(json.dumps({"log_n": lg, "n_gpus": world, "points_tiled": reps > 1, "msm_g1_ms_incl_h2d": ms, "msm_fq_mul_per_s": n * 16 * 10 / (ms * 1e-3),
                               "ntt_ms_per_gpu": ntt_ms, "result_sha": __import__("hashlib").sha256(res).hexdigest()[:16]}), flush=True)
     dist.destroy_process_group()
 

@@ -1,9 +1,8 @@
 #!/usr/bin/env python3
 """zkb-compute-witness: the file-level face of the witness side, options and defaults of `zokrates compute-witness`
 (/root/reference/zokrates_cli/src/ops/compute_witness.rs:16-75; raw `-a` / `--stdin` arguments — the ABI (JSON) input
-format belongs to the compiler front end and is out of scope).  Reads the compiled program (`out`), evaluates it — on the GPU
-level by level when the program is constraint-defined (`zkb_witness_eval`), with the host interpreter when it uses solver
-directives, as the reference does — and writes the binary `witness` (ir/witness.rs:44-53), optionally its JSON form and the
+format belongs to the compiler front end and is out of scope).  Reads the compiled program (`out`), evaluates it on the GPU level by
+level (`zkb_prog_compute_witness`: constraints assign or check, solver directives run the kernels of csrc/solvers.cuh) and writes the binary `witness` (ir/witness.rs:44-53), optionally its JSON form and the
 circom `.wtns` file.
 
     python tools/zkb_compute_witness.py -i out -o witness -a 337 113569 [--json] [--circom-witness out.wtns]
@@ -23,7 +22,8 @@ def main(argv=None) -> int:
     ap.add_argument("-a", "--arguments", nargs="*", default=None, help="Arguments for the program's main function: a space-separated list of field elements like `-a 1 2 3`")
     ap.add_argument("--stdin", action="store_true", help="Read arguments from stdin")
     ap.add_argument("--json", action="store_true", help="Write witness in a json format for debugging purposes")
-    ap.add_argument("--host", action="store_true", help="Force the host interpreter")
+    ap.add_argument("--host", action="store_true", help="Force the host interpreter (Python mirror of the reference interpreter)")
+    ap.add_argument("--try-out-of-range", action="store_true", help="Interpreter::try_out_of_range: second Bits decomposition")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args(argv)
 
@@ -32,7 +32,8 @@ def main(argv=None) -> int:
 
     try:
         with open(args.input, "rb") as f:
-            prog = zir.read_prog(f.read())
+            data = f.read()
+        prog = zir.read_prog(data)
     except OSError as why:
         raise SystemExit(f"Could not open {args.input}: {why.strerror}")
     except zir.ZirFormatError as why:
@@ -52,12 +53,14 @@ def main(argv=None) -> int:
             inputs.append(v)
     except ValueError as why:
         raise SystemExit(f"Could not parse argument: {why}")
+    from zokrates_b200 import backend
+    from zokrates_b200._lib import ZkbError
     try:
-        if args.host or any(isinstance(s, ir.Directive) for s in prog.statements):
-            witness = ir.Interpreter().execute(prog, inputs)
-        else:
-            witness = witness_gpu.generate_witness(prog, inputs)
-    except (ValueError, ir.UnsatisfiedConstraint, NotImplementedError) as why:
+        if args.host:
+            witness = ir.Interpreter(args.try_out_of_range).execute(prog, inputs)
+        else:   # the library runs the statements level by level on the GPU, solver directives included
+            witness = ir.Witness.read(backend.B200.compute_witness_files(data, inputs, prog.curve, args.try_out_of_range), prog.curve)
+    except (ValueError, ir.UnsatisfiedConstraint, NotImplementedError, ZkbError) as why:
         raise SystemExit(f"Execution failed: {why}")
     if args.verbose:
         print(f"\nWitness: \n{[str(v) for v in witness.return_values()]}\n")

@@ -23,10 +23,13 @@ def main(argv=None) -> int:
     ap.add_argument("-s", "--proving-scheme", default="g16", choices=["g16"], help="Proving scheme to use to generate the proof")
     ap.add_argument("-e", "--entropy", default=None, help="User provided randomness")
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--tables", type=int, default=0, choices=[0, 1],
+                    help="build the HBM window tables for this key (pays off from about a hundred proofs per key on; a one-shot process proves without)")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args(argv)
 
-    from zokrates_b200 import backend, ir, rng, zir
+    from zokrates_b200 import backend, rng, zir
+    from zokrates_b200._lib import ZkbError
 
     def slurp(path):
         try:
@@ -35,18 +38,22 @@ def main(argv=None) -> int:
         except OSError as why:
             raise SystemExit(f"Could not open {path}: {why.strerror}")
 
+    out_bytes = slurp(args.input)
     try:
-        prog = zir.read_prog(slurp(args.input))
+        curve_name = zir.read_header(out_bytes)[0]          # only the header is read here; the library parses the rest
     except zir.ZirFormatError as why:
         raise SystemExit(str(why))
     print("Generating proof...")
-    try:
-        witness = ir.Witness.read(slurp(args.witness), prog.curve)
-    except ValueError as why:
-        raise SystemExit(f"Could not load witness: {why}")
+    witness_bytes = slurp(args.witness)
     pk = slurp(args.proving_key_path)
     r = rng.get_rng_from_entropy(args.entropy) if args.entropy is not None else rng.StdRng.from_entropy()
-    proof = backend.B200.generate_proof(prog, witness, pk, r, device=args.device)
+    timings = {}
+    try:
+        from zokrates_b200._lib import OPT_TABLES
+        backend.context(curve_name, args.device).set_option(OPT_TABLES, args.tables)
+        proof = backend.B200.generate_proof_files(out_bytes, witness_bytes, pk, r, curve=curve_name, device=args.device, timings=timings)
+    except ZkbError as why:
+        raise SystemExit(f"Could not generate the proof: {why}")
     text = proof.to_tagged_json()
     try:
         with open(args.proof_path, "w") as f:
@@ -55,6 +62,7 @@ def main(argv=None) -> int:
         raise SystemExit(f"Could not write to {args.proof_path}: {why.strerror}")
     if args.verbose:
         print("Proof:\n" + text)
+        print("timings: " + ", ".join(f"{k} {v:.3f}" for k, v in timings.items()))
     print(f"Proof written to '{args.proof_path}'")
     return 0
 

@@ -28,9 +28,11 @@ SYMBOLS = [
     "zkb_groth16_prove_end", "zkb_groth16_finalize_prepare", "zkb_r1cs_check", "zkb_witness_eval",
     "zkb_pk_table_info", "zkb_ctx_set_option", "zkb_groth16_prove_submit", "zkb_groth16_prove_collect",
     "zkb_groth16_prove_collect_partial", "zkb_groth16_prove_begin_async", "zkb_groth16_prove_end_async",
+    "zkb_prog_load", "zkb_prog_info", "zkb_prog_free", "zkb_prog_compute_witness", "zkb_prog_set_witness",
+    "zkb_prog_public_inputs",
 ]
 
-OPT_TABLES, OPT_TABLE_MIN_LOG, OPT_TABLE_C, OPT_Z_MODE, OPT_NTT_TILE_MIN, OPT_NTT_MAX_S, OPT_BITSUM_RADIX = 1, 2, 3, 4, 5, 6, 7
+OPT_TABLES, OPT_TABLE_MIN_LOG, OPT_TABLE_C, OPT_Z_MODE, OPT_NTT_TILE_MIN, OPT_NTT_MAX_S, OPT_BITSUM_RADIX, OPT_PK_CACHE, OPT_NTT_KERNEL = 1, 2, 3, 4, 5, 6, 7, 8, 9
 TABLE_STATUS = {0: "none", 1: "built", 2: "below-min-size", 3: "no-memory", 4: "disabled", 5: "no-window"}
 
 
@@ -92,6 +94,13 @@ class Library:
         d.zkb_groth16_finalize_prepare.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         d.zkb_r1cs_check.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, _u64p]
         d.zkb_witness_eval.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, _u64p]
+        d.zkb_prog_load.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, _u64p]
+        d.zkb_prog_info.argtypes = [C.c_void_p, C.c_uint64, _u64p]
+        d.zkb_prog_free.argtypes = [C.c_void_p, C.c_uint64]
+        d.zkb_prog_compute_witness.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_size_t,
+                                               C.POINTER(C.c_size_t), _u64p]
+        d.zkb_prog_set_witness.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t]
+        d.zkb_prog_public_inputs.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, _u64p]
         d.zkb_msm_g1.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         d.zkb_msm_g2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         d.zkb_ntt.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32]
@@ -335,6 +344,49 @@ class Context:
         self.lib.check(self.lib.dll.zkb_witness_eval(self.h, r1cs, z.ctypes.data, len(level_ptr) - 1, level_ptr.ctypes.data,
                                                      rows.ctypes.data, out_var.ctypes.data, C.byref(first)))
         return z
+
+    # -- compiled programs (native `out` / witness-file front door)
+    PROG_INFO = ("constraints", "instance", "witness", "arguments", "returns", "directives", "levels", "r1cs", "extra_variables",
+                 "unsupported_directives", "public_arguments", "schedulable")
+
+    def prog_load(self, out_bytes: bytes) -> int:
+        buf = np.frombuffer(out_bytes, dtype=np.uint8)
+        h = C.c_uint64(0)
+        self.lib.check(self.lib.dll.zkb_prog_load(self.h, buf.ctypes.data, len(buf), C.byref(h)))
+        return h.value
+
+    def prog_info(self, prog: int) -> dict:
+        out = (C.c_uint64 * 12)()
+        self.lib.check(self.lib.dll.zkb_prog_info(self.h, prog, out))
+        return dict(zip(self.PROG_INFO, [int(x) for x in out]))
+
+    def prog_free(self, prog: int):
+        self.lib.check(self.lib.dll.zkb_prog_free(self.h, prog))
+
+    def prog_compute_witness(self, prog: int, inputs, try_out_of_range: bool = False) -> bytes:
+        """`Interpreter::execute` on the device; returns the witness FILE bytes.  ZkbError(ZKB_E_UNSAT) on a violated constraint."""
+        arr = fr_array([int(x) for x in inputs]) if len(inputs) else np.zeros((0, 4), dtype=np.uint64)
+        info = self.prog_info(prog)
+        cap = 8 + 40 * (info["instance"] + info["witness"] + info["extra_variables"])
+        out = np.zeros(cap, dtype=np.uint8)
+        n = C.c_size_t(0)
+        first = C.c_uint64(0)
+        self.lib.check(self.lib.dll.zkb_prog_compute_witness(self.h, prog, arr.ctypes.data if len(arr) else None, len(arr),
+                                                             1 if try_out_of_range else 0, out.ctypes.data, cap, C.byref(n), C.byref(first)))
+        return out[:n.value].tobytes()
+
+    def prog_set_witness(self, prog: int, witness_bytes: bytes):
+        buf = np.frombuffer(witness_bytes, dtype=np.uint8)
+        self.lib.check(self.lib.dll.zkb_prog_set_witness(self.h, prog, buf.ctypes.data, len(buf)))
+
+    def prog_public_inputs(self, prog: int):
+        n = C.c_uint64(0)
+        self.lib.check(self.lib.dll.zkb_prog_public_inputs(self.h, prog, None, 0, C.byref(n)))
+        if n.value == 0:
+            return []
+        out = np.zeros((max(n.value, 1), 4), dtype=np.uint64)
+        self.lib.check(self.lib.dll.zkb_prog_public_inputs(self.h, prog, out.ctypes.data, n.value, C.byref(n)))
+        return fr_from_array(out[:n.value])
 
     # -- building blocks
     def msm(self, group: int, points: bytes, scalars: np.ndarray) -> bytes:

@@ -107,6 +107,55 @@ class B200:
         return Proof.from_raw(c, raw, inputs)
 
     @staticmethod
+    def generate_proof_files(out_bytes: bytes, witness_bytes: bytes, proving_key, rng: StdRng, curve="bn128", device: int = 0,
+                             lib: Optional[_lib.Library] = None, timings: Optional[dict] = None) -> Proof:
+        """`generate_proof` for the three FILES the CLI hands over (zokrates_cli/src/ops/generate_proof.rs:152-202): the
+        compiled program, the binary witness and `proving.key`.  Nothing is interpreted in Python: the library parses the
+        program and the witness natively (`zkb_prog_load`, `zkb_prog_set_witness`), synthesises the R1CS in ark order and
+        proves from the resident assignment.  Repeated calls with the same key bytes reuse the resident key and its window
+        tables (ZKB_OPT_PK_CACHE).  Same proof as `generate_proof(read_prog(out), Witness.read(witness), ...)`."""
+        import time
+        c = _curve(curve)
+        ctx = context(c, device, lib)
+        pk_bytes = proving_key.read() if hasattr(proving_key, "read") else proving_key
+        r = fr_rand(c, rng)
+        s = fr_rand(c, rng)
+        t0 = time.perf_counter()
+        with ctx.lock:
+            prog = ctx.prog_load(out_bytes)
+            pk_h = None
+            try:
+                info = ctx.prog_info(prog)
+                t1 = time.perf_counter()
+                ctx.prog_set_witness(prog, witness_bytes)
+                inputs = ctx.prog_public_inputs(prog)
+                t2 = time.perf_counter()
+                pk_h = ctx.pk_load(pk_bytes, 0, 1)
+                t3 = time.perf_counter()
+                raw = ctx.prove_resident(pk_h, info["r1cs"], r, s)
+                t4 = time.perf_counter()
+            finally:
+                if pk_h:
+                    ctx.pk_free(pk_h)
+                ctx.prog_free(prog)
+        if timings is not None:
+            timings.update(prog_load_s=t1 - t0, witness_s=t2 - t1, pk_load_s=t3 - t2, prove_s=t4 - t3)
+        return Proof.from_raw(c, raw, inputs)
+
+    @staticmethod
+    def compute_witness_files(out_bytes: bytes, inputs, curve="bn128", try_out_of_range: bool = False, device: int = 0,
+                              lib: Optional[_lib.Library] = None) -> bytes:
+        """`zokrates compute-witness` on the device: program file + argument values -> witness file bytes
+        (`Interpreter::execute`, zokrates_interpreter/src/lib.rs:40-138, with the solver kernels of csrc/solvers.cuh)."""
+        ctx = context(_curve(curve), device, lib)
+        with ctx.lock:
+            prog = ctx.prog_load(out_bytes)
+            try:
+                return ctx.prog_compute_witness(prog, inputs, try_out_of_range)
+            finally:
+                ctx.prog_free(prog)
+
+    @staticmethod
     def setup(program: Prog, trapdoor, device: int = 0, lib: Optional[_lib.Library] = None) -> SetupKeypair:
         """`NonUniversalBackend::setup`.  `trapdoor` is either an `StdRng` (alpha, beta, gamma, delta, tau and
         the two generator scalars are drawn from it with `fr_rand`, in that order) or 7 explicit integers."""

@@ -156,6 +156,8 @@ int32_t zkb_ctx_set_option(zkb_ctx* ctx, int32_t opt, int64_t value) {
       case ZKB_OPT_Z_MODE: if (value < 0 || value > 2) throw Error(ZKB_E_ARG, "ZKB_OPT_Z_MODE: 0, 1 or 2"); o.z_mode = value; break;
       case ZKB_OPT_NTT_TILE_MIN: if (value < 0 || value > 64) throw Error(ZKB_E_ARG, "ZKB_OPT_NTT_TILE_MIN"); o.ntt_tile_min = value; break;
       case ZKB_OPT_NTT_MAX_S: if (value < 1 || value > 10) throw Error(ZKB_E_ARG, "ZKB_OPT_NTT_MAX_S: 1..10"); o.ntt_max_s = value; break;
+      case ZKB_OPT_NTT_KERNEL: if (value != 1 && value != 2) throw Error(ZKB_E_ARG, "ZKB_OPT_NTT_KERNEL: 1 or 2"); o.ntt_kernel = value; break;
+      case ZKB_OPT_PK_CACHE: if (value < 0 || value > 1) throw Error(ZKB_E_ARG, "ZKB_OPT_PK_CACHE: 0 or 1"); o.pk_cache = value; break;
       case ZKB_OPT_BITSUM_RADIX: if (value != 2 && value != 8) throw Error(ZKB_E_ARG, "ZKB_OPT_BITSUM_RADIX: 2 or 8"); o.bitsum_radix = value; break;
       default: throw Error(ZKB_E_ARG, "unknown option");
     }
@@ -308,6 +310,37 @@ int32_t zkb_witness_eval(zkb_ctx* ctx, uint64_t r1cs, uint64_t* z_inout, uint32_
     uint64_t f = ctx->eng->witness_eval(r1cs, z_inout, n_levels, level_ptr, rows, out_var);
     if (first_unsatisfied) *first_unsatisfied = f;
     if (f != ~0ull) throw Error(ZKB_E_UNSAT, "constraint " + std::to_string(f) + " is not satisfied");
+  });
+}
+int32_t zkb_prog_load(zkb_ctx* ctx, const uint8_t* out_bytes, size_t len, uint64_t* h) {
+  return guard(ctx, [&] {
+    if (!out_bytes || !h) throw Error(ZKB_E_ARG, "null argument");
+    *h = ctx->eng->prog_load(out_bytes, len, ctx->curve);
+  });
+}
+int32_t zkb_prog_info(zkb_ctx* ctx, uint64_t h, uint64_t out[12]) {
+  return guard(ctx, [&] { if (!out) throw Error(ZKB_E_ARG, "null"); ctx->eng->prog_info(h, out); });
+}
+int32_t zkb_prog_free(zkb_ctx* ctx, uint64_t h) { return guard(ctx, [&] { ctx->eng->prog_free(h); }); }
+int32_t zkb_prog_compute_witness(zkb_ctx* ctx, uint64_t h, const uint64_t* inputs, uint64_t n_inputs, uint32_t flags,
+                                 uint8_t* witness_out, size_t witness_cap, size_t* witness_len, uint64_t* first_unsatisfied) {
+  return guard(ctx, [&] {
+    if (!inputs && n_inputs) throw Error(ZKB_E_ARG, "null argument");
+    uint64_t f = ctx->eng->prog_compute_witness(h, inputs, n_inputs, flags, witness_out, witness_cap, witness_len);
+    if (first_unsatisfied) *first_unsatisfied = f;
+    if (f != ~0ull) throw Error(ZKB_E_UNSAT, "constraint " + std::to_string(f) + " is not satisfied");
+  });
+}
+int32_t zkb_prog_set_witness(zkb_ctx* ctx, uint64_t h, const uint8_t* witness_bytes, size_t len) {
+  return guard(ctx, [&] {
+    if (!witness_bytes) throw Error(ZKB_E_ARG, "null argument");
+    ctx->eng->prog_set_witness(h, witness_bytes, len);
+  });
+}
+int32_t zkb_prog_public_inputs(zkb_ctx* ctx, uint64_t h, uint64_t* out, uint64_t cap, uint64_t* count) {
+  return guard(ctx, [&] {
+    uint64_t n = ctx->eng->prog_public_inputs(h, out, cap);
+    if (count) *count = n;
   });
 }
 int32_t zkb_field_op(zkb_ctx* ctx, int32_t field, int32_t op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n) {

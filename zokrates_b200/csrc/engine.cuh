@@ -16,6 +16,8 @@
 #include "fp64.cuh"
 #include "msm.cuh"
 #include "ntt.cuh"
+#include "ntt_tile.cuh"
+#include "solvers.cuh"
 #include "rt.cuh"
 #include "engine_base.cuh"
 
@@ -30,7 +32,7 @@ struct k_fr_convert; struct k_spmv; struct k_ntt_dif; struct k_ntt_dit; struct k
 struct k_ntt_table; struct k_qap_pointwise; struct k_msm_digits; struct k_msm_scatter; struct k_msm_accum1;
 struct k_msm_accum2; struct k_msm_bitsum; struct k_pk_convert; struct k_final_a; struct k_final_b;
 struct k_final_c; struct k_final_d; struct k_point_out; struct k_field_op; struct k_setup_scalars; struct k_fixed_base;
-struct k_to_affine; struct k_copy; struct k_msm_view; struct k_msm_table; struct k_ntt_dif_tile; struct k_ntt_dit_tile; struct k_witness_level;
+struct k_to_affine; struct k_copy; struct k_msm_view; struct k_solver_level; struct k_msm_table; struct k_ntt_dif_tile; struct k_ntt_dit_tile; struct k_witness_level;
 
 // ---------------------------------------------------------------------------------------------
 // stage timer: CUDA events on the engine stream (no-op in the host emulation)
@@ -387,6 +389,17 @@ class Engine : public EngineBase {
   uint32_t ntt_tile_min() const { return opts.ntt_tile_min < (int64_t)NTT_TILE_LOG ? NTT_TILE_LOG : (uint32_t)opts.ntt_tile_min; }
   uint32_t ntt_max_s() const { return opts.ntt_max_s < 5 ? 5u : (uint32_t)opts.ntt_max_s; }
   bool ntt_tiled(uint32_t log_n) const { return log_n >= ntt_tile_min(); }
+  int sm_count_ = 0;
+  int sm_count() {
+#if !defined(ZKB_EMU)
+    if (!sm_count_) {
+      int dev = 0;
+      ZKB_CUDA(cudaGetDevice(&dev));
+      ZKB_CUDA(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, dev));
+    }
+#endif
+    return sm_count_ ? sm_count_ : 1;
+  }
 
   // natural -> bit-reversed
   void ntt_dif(Fr* x, const Fr* tw, uint32_t log_n) {
@@ -395,6 +408,12 @@ class Engine : public EngineBase {
     if (np) {
       const size_t tiles = ((size_t)1 << log_n) >> NTT_TILE_LOG;
       const Fr* nul = nullptr;
+#if !defined(ZKB_EMU)
+      if (opts.ntt_kernel == 2) {           // four-step twiddles, cp.async tile load, padded planes (ntt_tile.cuh)
+        for (uint32_t i = 0; i < np; i++) launch_ntt_tile2<Fr, false>(st_, x, tw, nul, ps[i], tiles, sm_count());
+        return;
+      }
+#endif
       for (uint32_t i = 0; i < np; i++) {   // top stage bits first
         NttPass p = ps[i];
         launch_block<k_ntt_dif_tile, NTT_BLOCK, NTT_TILE * sizeof(Fr)>(st_, tiles, p.nk + 2, ZKB_LAMBDA(uint32_t b, uint32_t t, uint32_t ph, void* sm) {
@@ -421,6 +440,12 @@ class Engine : public EngineBase {
     const uint32_t np = ntt_tiled(log_n) ? ntt_plan_passes(log_n, ntt_max_s(), ps) : 0;
     if (np) {
       const size_t tiles = ((size_t)1 << log_n) >> NTT_TILE_LOG;
+#if !defined(ZKB_EMU)
+      if (opts.ntt_kernel == 2) {
+        for (uint32_t i = np; i-- > 0;) launch_ntt_tile2<Fr, true>(st_, x, tw, (i == np - 1) ? scale : nullptr, ps[i], tiles, sm_count());
+        return;
+      }
+#endif
       for (uint32_t i = np; i-- > 0;) {     // low stage bits first
         NttPass p = ps[i];
         const Fr* sc = (i == np - 1) ? scale : nullptr;
@@ -731,6 +756,171 @@ class Engine : public EngineBase {
     return first == 0xFFFFFFFFu ? ~0ull : (uint64_t)first;
   }
 
+  // ------------------------------------------------------------------------------ compiled programs (`out` files)
+  // zkb_prog_load: parse the program file, synthesise the R1CS in ark order and keep it resident (an ordinary R1CS handle),
+  // keep the directive tables and the level schedule on the device.  zkb_prog_compute_witness then runs the statements
+  // level by level: constraints through witness_level_body (assign or check), directives through solver_body.
+  struct ProgDev {
+    ProgData d;
+    DevBuf<uint32_t> kind, arg, in_ptr, out_ptr, out_cols, lc_ptr, lc_col, rows, out_var, dirs;
+    DevBuf<Fr> lc_val;
+    std::vector<uint64_t> z_host;   // the assignment of the last compute_witness / set_witness (m x 4 words), for public_inputs
+  };
+  std::map<uint64_t, std::unique_ptr<ProgDev>> progs_;
+  ProgDev& get_prog(uint64_t h) {
+    auto it = progs_.find(h);
+    if (it == progs_.end()) throw Error(ZKB_E_ARG, "unknown program handle");
+    return *it->second;
+  }
+  static void fr_modulus(uint32_t mod[8]) { for (int i = 0; i < 8; i++) mod[i] = Fr::Params::mod(i); }
+  template <class T>
+  void upload(DevBuf<T>& buf, const std::vector<T>& v) {
+    buf.alloc(v.size() ? v.size() : 1);
+    h2d(st_, buf.p, v.data(), v.size() * sizeof(T));
+  }
+
+  uint64_t prog_load(const uint8_t* data, size_t len, int curve) override {
+    std::unique_ptr<ProgDev> p(new ProgDev());
+    uint32_t mod[8];
+    fr_modulus(mod);
+    prog_parse(data, len, curve, mod, p->d);
+    prog_schedule(p->d);
+    ProgData& d = p->d;
+    const uint64_t* rp[3] = {d.rowptr[0].data(), d.rowptr[1].data(), d.rowptr[2].data()};
+    const uint32_t* cl[3] = {d.col[0].data(), d.col[1].data(), d.col[2].data()};
+    const uint64_t* vl[3] = {d.val[0].data(), d.val[1].data(), d.val[2].data()};
+    d.r1cs = r1cs_load(d.N, d.ni, d.nw, rp, cl, vl);
+    try {
+      upload(p->kind, d.d_kind); upload(p->arg, d.d_arg); upload(p->in_ptr, d.d_in_ptr); upload(p->out_ptr, d.d_out_ptr);
+      upload(p->out_cols, d.d_out_cols); upload(p->lc_ptr, d.lc_ptr); upload(p->lc_col, d.lc_col);
+      upload(p->rows, d.rows); upload(p->out_var, d.out_var); upload(p->dirs, d.dirs);
+      const size_t nt = d.lc_col.size();
+      p->lc_val.alloc(nt ? nt : 1);
+      h2d(st_, p->lc_val.p, d.lc_val.data(), nt * FRB);
+      convert(p->lc_val.p, p->lc_val.p, 0, nt);
+      stream_sync(st_);
+    } catch (...) {
+      r1cs_free(d.r1cs);
+      throw;
+    }
+    // the matrices now live on the device (and, for setup, in the R1cs host copy): drop the parser's copies of the values
+    for (int k = 0; k < 3; k++) { std::vector<uint64_t>().swap(d.val[k]); }
+    std::vector<uint64_t>().swap(d.lc_val);
+    uint64_t h = next_handle_++;
+    progs_[h] = std::move(p);
+    return h;
+  }
+  // out: constraints, instance count (incl. one), witness count, arguments, return values, directives, levels, R1CS handle,
+  //      extra (directive-only) variables, directives without a device solver, public argument count, schedulable (0/1)
+  void prog_info(uint64_t h, uint64_t out[12]) override {
+    const ProgData& d = get_prog(h).d;
+    uint64_t pub = 0;
+    for (uint8_t pr : d.arg_private) pub += pr ? 0 : 1;
+    out[0] = d.N; out[1] = d.ni; out[2] = d.nw; out[3] = d.arg_ids.size(); out[4] = d.n_ret; out[5] = d.d_kind.size();
+    out[6] = d.n_levels; out[7] = d.r1cs; out[8] = d.m_ext - d.m; out[9] = d.n_unsupported; out[10] = pub;
+    out[11] = d.schedule_error.empty() ? 1 : 0;
+  }
+  void prog_free(uint64_t h) override {
+    ProgDev& p = get_prog(h);
+    r1cs_free(p.d.r1cs);
+    progs_.erase(h);
+  }
+
+  // inputs: one canonical field element per program argument.  Returns the first unsatisfied constraint or ~0; on success
+  // the assignment stays resident in the program's R1CS (zkb_groth16_prove_resident can follow) and `wit_out` receives the
+  // witness FILE bytes (ir/witness.rs:44-53) when it is non-null.
+  uint64_t prog_compute_witness(uint64_t h, const uint64_t* inputs, uint64_t n_inputs, uint32_t flags, uint8_t* wit_out, size_t cap,
+                                size_t* wit_len) override {
+    ProgDev& p = get_prog(h);
+    const ProgData& d = p.d;
+    if (n_inputs != d.arg_ids.size())
+      throw Error(ZKB_E_ARG, "WrongInputCount: expected " + std::to_string(d.arg_ids.size()) + ", received " + std::to_string(n_inputs));
+    if (!d.schedule_error.empty()) throw Error(ZKB_E_FORMAT, "program cannot be executed: " + d.schedule_error);
+    if (d.n_unsupported) throw Error(ZKB_E_ARG, "the program calls a solver that has no device path (Zir function / embed gadget)");
+    uint32_t mod[8];
+    fr_modulus(mod);
+    for (uint64_t i = 0; i < n_inputs; i++)
+      if (!prog_detail::canonical((const uint8_t*)(inputs + 4 * i), mod)) throw Error(ZKB_E_ARG, "input is not a canonical field element");
+    R1cs& r = get_r1cs(d.r1cs);
+    std::vector<uint64_t> z((size_t)d.m_ext * 4, 0);
+    z[0] = 1;
+    for (uint64_t i = 0; i < n_inputs; i++) memcpy(&z[4 * (size_t)d.arg_cols[i]], inputs + 4 * i, 32);
+    DevBuf<Fr> zc(d.m_ext), zm(d.m_ext);
+    DevBuf<uint32_t> d_flag(1);
+    StageTimer tm(st_);
+    h2d(st_, zc.p, z.data(), d.m_ext * FRB);
+    dev_fill_ff(st_, d_flag.p, 4);
+    tm.begin("witness_eval");
+    convert(zc.p, zm.p, 0, d.m_ext);
+    const uint32_t* rpA = r.rowptr[0].p; const uint32_t* clA = r.col[0].p; const Fr* vlA = r.val[0].p;
+    const uint32_t* rpB = r.rowptr[1].p; const uint32_t* clB = r.col[1].p; const Fr* vlB = r.val[1].p;
+    const uint32_t* rpC = r.rowptr[2].p; const uint32_t* clC = r.col[2].p; const Fr* vlC = r.val[2].p;
+    Fr* zp = zm.p;
+    uint32_t* flag = d_flag.p;
+    const uint32_t* pr = p.rows.p; const uint32_t* po = p.out_var.p; const uint32_t* pd = p.dirs.p;
+    const uint32_t* kd = p.kind.p; const uint32_t* ar = p.arg.p; const uint32_t* ip = p.in_ptr.p; const uint32_t* op = p.out_ptr.p;
+    const uint32_t* oc = p.out_cols.p; const uint32_t* lp = p.lc_ptr.p; const uint32_t* lc = p.lc_col.p; const Fr* lv = p.lc_val.p;
+    for (uint32_t l = 1; l <= d.n_levels; l++) {
+      const uint32_t rlo = d.row_level_ptr[l - 1], rhi = d.row_level_ptr[l], dlo = d.dir_level_ptr[l - 1], dhi = d.dir_level_ptr[l];
+      if (rhi > rlo)
+        launch<k_witness_level>(st_, rhi - rlo, ZKB_LAMBDA(size_t t) {
+          witness_level_body<Fr>(rpA, clA, vlA, rpB, clB, vlB, rpC, clC, vlC, zp, pr, po, rlo, rhi, flag, (uint32_t)t);
+        });
+      if (dhi > dlo)
+        launch<k_solver_level, 64>(st_, dhi - dlo, ZKB_LAMBDA(size_t t) {
+          solver_body<Fr>(kd, ar, ip, op, oc, lp, lc, lv, zp, pd, dlo, dhi, flags, (uint32_t)t);
+        });
+    }
+    convert(zm.p, zc.p, 1, d.m_ext);
+    tm.end();
+    uint32_t first = 0;
+    d2h(st_, &first, d_flag.p, 4);
+    d2h(st_, z.data(), zc.p, d.m_ext * FRB);
+    d2d(st_, r.z_canon.p, zc.p, d.m * FRB);
+    stream_sync(st_);
+    tm.collect(timings);
+    if (first != 0xFFFFFFFFu) return (uint64_t)first;
+    r.has_z = true;
+    r.sparse_z = assignment_is_sparse(z.data(), d.m);
+    p.z_host.assign(z.begin(), z.begin() + (size_t)d.m * 4);
+    if (wit_len) *wit_len = 8 + 40 * (size_t)std::count(d.defined.begin(), d.defined.end(), (uint8_t)1);
+    if (wit_out) {
+      std::vector<uint8_t> bytes;
+      witness_write(d, z.data(), bytes);
+      if (bytes.size() > cap) throw Error(ZKB_E_ARG, "witness buffer too small");
+      memcpy(wit_out, bytes.data(), bytes.size());
+    }
+    return ~0ull;
+  }
+  // witness file -> resident assignment of the program's R1CS (what `generate-proof -w witness` reads, generate_proof.rs:161-166)
+  void prog_set_witness(uint64_t h, const uint8_t* wit, size_t len) override {
+    ProgDev& p = get_prog(h);
+    uint32_t mod[8];
+    fr_modulus(mod);
+    witness_parse(p.d, wit, len, mod, p.z_host);
+    set_assignment(p.d.r1cs, p.z_host.data());
+  }
+  // public arguments in declaration order, then the return values ~out_0.. (ir/mod.rs:278-288), from the current assignment
+  uint64_t prog_public_inputs(uint64_t h, uint64_t* out, uint64_t cap) override {
+    ProgDev& p = get_prog(h);
+    const ProgData& d = p.d;
+    if (p.z_host.size() != (size_t)d.m * 4) throw Error(ZKB_E_ARG, "the program has no assignment yet");
+    std::vector<uint32_t> cols;
+    for (size_t i = 0; i < d.arg_ids.size(); i++) if (!d.arg_private[i]) cols.push_back(d.arg_cols[i]);
+    for (uint32_t k = 0; k < d.n_ret; k++) {
+      const int64_t id = -(int64_t)k - 1;
+      uint32_t c = 0;
+      for (; c < d.ni; c++) if (d.var_of_col[c] == id) break;
+      if (c == d.ni) throw Error(ZKB_E_FORMAT, "return value ~out_" + std::to_string(k) + " does not occur in the constraints");
+      cols.push_back(c);
+    }
+    if (out) {
+      if (cols.size() > cap) throw Error(ZKB_E_ARG, "public input buffer too small");
+      for (size_t i = 0; i < cols.size(); i++) memcpy(out + 4 * i, &p.z_host[4 * (size_t)cols[i]], 32);
+    }
+    return cols.size();
+  }
+
   // ------------------------------------------------------------------------------ MSM
 
   void plan_build(MsmPlan& pl, const Fr* scalars, uint64_t n, uint32_t nviews = 1, const uint8_t* skip = nullptr,
@@ -985,8 +1175,34 @@ class Engine : public EngineBase {
     DevBuf<uint8_t> skip;                        // per assignment index: bit0 = a_query point is infinity, bit1 = b_query point is infinity
     HG1A h_fixed1[5];                            // host copies (Montgomery form) for the serial tail
     HG2A h_fixed2[3];
+    uint64_t fp[2] = {0, 0};                     // content fingerprint (key bytes, shard, table options): the cache key
   };
-  std::map<uint64_t, std::unique_ptr<Pk>> pks_;
+  // Handles share keys by CONTENT: the reference's `Backend::generate_proof` is static and receives the key bytes on every
+  // call (zokrates_ark/src/groth16.rs:40-42), so the trait-shaped use is pk_load / prove / pk_free per proof.  A second load of
+  // the same bytes (same shard, same table options) returns a new handle onto the resident key, and the last key released
+  // stays resident (`idle_pk_`) until a different key needs the memory — the 0.9 s / 5.6 GB of window tables are built once.
+  std::map<uint64_t, std::shared_ptr<Pk>> pks_;
+  std::shared_ptr<Pk> idle_pk_;
+  // 128-bit fingerprint of the key bytes: four multiply-rotate lanes over 8-byte words (not cryptographic: a cache key for
+  // bytes the caller already trusts as its proving key)
+  static void fingerprint(const uint8_t* data, size_t len, uint64_t salt, uint64_t out[2]) {
+    uint64_t h[4] = {0x9E3779B97F4A7C15ull ^ salt, 0xC2B2AE3D27D4EB4Full + len, 0x165667B19E3779F9ull, 0x27D4EB2F165667C5ull ^ (salt << 17)};
+    const uint64_t k1 = 0xff51afd7ed558ccdull, k2 = 0xc4ceb9fe1a85ec53ull;
+    size_t i = 0;
+    for (; i + 32 <= len; i += 32) {
+      uint64_t w[4];
+      memcpy(w, data + i, 32);
+      for (int l = 0; l < 4; l++) { uint64_t x = (h[l] ^ w[l]) * k1; h[l] = ((x << 29) | (x >> 35)) + k2; }
+    }
+    uint8_t tail[32] = {0};
+    memcpy(tail, data + i, len - i);
+    uint64_t w[4];
+    memcpy(w, tail, 32);
+    for (int l = 0; l < 4; l++) { uint64_t x = (h[l] ^ w[l]) * k2; h[l] = ((x << 31) | (x >> 33)) * k1; }
+    auto mix = [&](uint64_t x) { x ^= x >> 33; x *= k1; x ^= x >> 29; x *= k2; x ^= x >> 32; return x; };
+    out[0] = mix(h[0] + mix(h[1])) ^ mix(h[2] ^ (h[3] << 1));
+    out[1] = mix(h[2] + mix(h[3] ^ k1)) + mix(h[0] ^ (h[1] >> 3));
+  }
   Pk& get_pk(uint64_t h) {
     auto it = pks_.find(h);
     if (it == pks_.end()) throw Error(ZKB_E_ARG, "unknown pk handle");
@@ -1082,6 +1298,27 @@ class Engine : public EngineBase {
 
   uint64_t pk_load(const uint8_t* pk, size_t len, uint32_t rank, uint32_t world) override {
     if (world == 0 || rank >= world) throw Error(ZKB_E_ARG, "bad rank/world");
+    uint64_t fp[2] = {0, 0};
+    if (opts.pk_cache) {
+      const uint64_t salt = ((uint64_t)rank << 48) ^ ((uint64_t)world << 32) ^ ((uint64_t)opts.tables << 24) ^ ((uint64_t)opts.table_c << 16) ^
+                            ((uint64_t)opts.table_min_log << 8);
+      fingerprint(pk, len, salt, fp);
+      std::shared_ptr<Pk> hit;
+      if (idle_pk_ && idle_pk_->fp[0] == fp[0] && idle_pk_->fp[1] == fp[1]) { hit = idle_pk_; idle_pk_.reset(); }
+      else for (auto& kv : pks_) if (kv.second->fp[0] == fp[0] && kv.second->fp[1] == fp[1]) { hit = kv.second; break; }
+      if (hit) {
+        timings.clear();
+        timings.push_back({"pk_cache_hit", 1.0});
+        uint64_t h = next_handle_++;
+        pks_[h] = hit;
+        return h;
+      }
+    }
+    if (idle_pk_) {   // a different key: release the cached one first (its fixed points may still feed host threads)
+      for (auto& sl : slots_) if (sl.fm.valid()) sl.fm.wait();
+      if (prepared_.fut.valid()) prepared_.fut.wait();
+      idle_pk_.reset();
+    }
     size_t off = 0;
     auto need = [&](size_t k) { if (off + k > len) throw Error(ZKB_E_FORMAT, "proving key truncated"); };
     auto take = [&](size_t k) { need(k); const uint8_t* p = pk + off; off += k; return p; };
@@ -1113,7 +1350,8 @@ class Engine : public EngineBase {
     if (off != len) throw Error(ZKB_E_FORMAT, "trailing bytes after proving key");
     if (ni < 1 || m < ni || ll != m - ni) throw Error(ZKB_E_FORMAT, "inconsistent query lengths");
 
-    std::unique_ptr<Pk> p(new Pk());
+    std::shared_ptr<Pk> p(new Pk());
+    p->fp[0] = fp[0]; p->fp[1] = fp[1];
     p->ni = ni; p->m = m; p->hl = hl; p->ll = ll; p->rank = rank; p->world = world;
     const uint64_t na = m - 1;  // pairs with assignment = z[1..]
     p->lo = na * rank / world; p->hi = na * (rank + 1) / world;
@@ -1199,7 +1437,12 @@ class Engine : public EngineBase {
       if (sl.fm.valid()) sl.fm.wait();     // a finished proof's host multiplications may still read the key's fixed points
     }
     if (prepared_.pk == h) { if (prepared_.fut.valid()) prepared_.fut.wait(); prepared_.pk = 0; }
-    pks_.erase(h);
+    auto it = pks_.find(h);
+    if (it == pks_.end()) throw Error(ZKB_E_ARG, "unknown pk handle");
+    std::shared_ptr<Pk> last = it->second;
+    pks_.erase(it);
+    if (opts.pk_cache && last.use_count() == 1 && (last->fp[0] | last->fp[1])) idle_pk_ = last;   // the last handle: stay resident
+
   }
 
   // ------------------------------------------------------------------------------ prove

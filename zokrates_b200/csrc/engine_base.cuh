@@ -15,6 +15,8 @@ struct Options {
   int64_t z_mode = 0;         // ZKB_OPT_Z_MODE: 0 sample the assignment, 1 always the shared-bucket table mode, 2 always per-window buckets
   int64_t ntt_tile_min = 10;  // ZKB_OPT_NTT_TILE_MIN: transforms of 2^k points and more use the shared-memory tile passes
   int64_t ntt_max_s = 10;     // ZKB_OPT_NTT_MAX_S: stage bits per tile pass
+  int64_t ntt_kernel = 2;     // ZKB_OPT_NTT_KERNEL: 2 = four-step twiddles / cp.async tile load (ntt_tile.cuh), 1 = the round-1 tile pass
+  int64_t pk_cache = 1;       // ZKB_OPT_PK_CACHE: share proving keys by content and keep the last released one resident
   int64_t bitsum_radix = 2;   // ZKB_OPT_BITSUM_RADIX: bucket-reduction levels of radix 2 (1 dependent addition per launch) or 8 (7)
 };
 
@@ -50,6 +52,13 @@ struct EngineBase {
   virtual void witness_map(uint64_t r1cs, const uint64_t* z, uint64_t* h_out, uint64_t cap) = 0;
   virtual uint64_t witness_eval(uint64_t r1cs, uint64_t* z_io, uint32_t n_levels, const uint32_t* level_ptr,
                                 const uint32_t* rows, const uint32_t* out_var) = 0;
+  virtual uint64_t prog_load(const uint8_t* data, size_t len, int curve) = 0;
+  virtual void prog_info(uint64_t h, uint64_t out[12]) = 0;
+  virtual void prog_free(uint64_t h) = 0;
+  virtual uint64_t prog_compute_witness(uint64_t h, const uint64_t* inputs, uint64_t n_inputs, uint32_t flags, uint8_t* wit_out,
+                                        size_t cap, size_t* wit_len) = 0;
+  virtual void prog_set_witness(uint64_t h, const uint8_t* wit, size_t len) = 0;
+  virtual uint64_t prog_public_inputs(uint64_t h, uint64_t* out, uint64_t cap) = 0;
   virtual void field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n) = 0;
   virtual size_t setup_size(uint64_t r1cs) = 0;
   virtual void setup(uint64_t r1cs, const uint64_t* trapdoor7, uint8_t* pk_out, size_t cap, size_t* len) = 0;

@@ -24,6 +24,34 @@ static __global__ void zkb_probe_imad(uint32_t iters, uint32_t seed, uint64_t* s
   for (int k = 0; k < 8; k++) s ^= acc[k];
   if (s == 0x1234567) sink[0] = s;
 }
+// kind 2: the same count of wide multiply-adds, but CARRY-CHAINED as a multi-limb multiplier needs them: rows of 8
+// (mad.lo.cc/madc.hi.cc, 6 x madc.lo.cc/madc.hi.cc, madc.lo.cc/madc.hi) = IMAD.WIDE.U32 followed by 7 IMAD.WIDE.U32.X with
+// predicate carries, 4 independent rows per thread.  ncu shows the .X form costs more fmaheavy-pipe cycles than the
+// carry-free one (profiles/r02_ncu_accum1_g2.md): this is the multiply-add rate a carry-propagating multiplication can reach.
+static __global__ void zkb_probe_imad_carry(uint32_t iters, uint32_t seed, uint64_t* sink) {
+  uint32_t a = seed + threadIdx.x, b = seed * 2654435761u + blockIdx.x;
+  uint32_t lo[4][8], hi[4][8];
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int k = 0; k < 8; k++) { lo[r][k] = a + k; hi[r][k] = b + r; }
+  for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      ptx::mad_wide_cc(lo[r][0], hi[r][0], a, b, lo[r][0], hi[r][0]);
+#pragma unroll
+      for (int k = 1; k < 7; k++) ptx::madc_wide_cc(lo[r][k], hi[r][k], a, b, lo[r][k], hi[r][k]);
+      ptx::madc_wide(lo[r][7], hi[r][7], a, b, lo[r][7], hi[r][7]);
+    }
+    a += lo[0][0];
+  }
+  uint64_t s = 0;
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= ((uint64_t)hi[r][k] << 32) | lo[r][k];
+  if (s == 0x1234567) sink[0] = s;
+}
 // kind 1: register-resident Montgomery multiplications, 2 independent chains per thread
 template <class F>
 static __global__ void zkb_probe_modmul(uint32_t iters, uint32_t seed, F* sink) {
@@ -54,6 +82,7 @@ inline double peak_probe(Stream st, int kind, uint32_t iters) {
   for (int rep = 0; rep < 2; rep++) {  // first repetition is the warm-up
     ZKB_CUDA(cudaEventRecord(a, st.s));
     if (kind == 0) zkb_probe_imad<<<blocks, block, 0, st.s>>>(iters, 12345u, sink.p);
+    else if (kind == 2) zkb_probe_imad_carry<<<blocks, block, 0, st.s>>>(iters, 12345u, sink.p);
     else zkb_probe_modmul<F><<<blocks, block, 0, st.s>>>(iters, 12345u, (F*)sink.p);
     ZKB_CUDA(cudaGetLastError());
     ZKB_CUDA(cudaEventRecord(b, st.s));
@@ -63,7 +92,7 @@ inline double peak_probe(Stream st, int kind, uint32_t iters) {
   ZKB_CUDA(cudaEventElapsedTime(&ms, a, b));
   cudaEventDestroy(a);
   cudaEventDestroy(b);
-  double per_thread = kind == 0 ? 8.0 * iters : 2.0 * iters;
+  double per_thread = kind == 0 ? 8.0 * iters : kind == 2 ? 32.0 * iters : 2.0 * iters;
   return per_thread * block * blocks / (ms * 1e-3);
 #else
   (void)st; (void)kind; (void)iters;

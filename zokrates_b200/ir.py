@@ -214,7 +214,19 @@ class UnsatisfiedConstraint(Exception):
 
 class Interpreter:
     """Witness generation restated from zokrates_interpreter/src/lib.rs (simple solvers only; `Zir`
-    folded functions and the embed gadgets stay with the reference's compiler front end)."""
+    folded functions and the embed gadgets stay with the reference's compiler front end).
+    `try_out_of_range` mirrors `Interpreter::try_out_of_range()` (lib.rs:32-38)."""
+
+    def __init__(self, try_out_of_range: bool = False):
+        self.should_try_out_of_range = try_out_of_range
+
+    @staticmethod
+    def try_solve_with_out_of_range_bits(c: Curve, bit_width: int, x: int) -> List[int]:
+        """lib.rs:140-165: the second decomposition x + r when it still fits `get_required_bits()` bits."""
+        req = c.r.bit_length()
+        cand = x % c.r + c.r
+        v = cand if cand < (1 << req) else x % c.r
+        return [0] * (bit_width - req) + [(v >> i) & 1 for i in range(req - 1, -1, -1)]
 
     @staticmethod
     def evaluate_lin(c: Curve, w: Witness, l: LinComb) -> int:
@@ -234,7 +246,7 @@ class Interpreter:
             return [0, 1] if x[0] % r == 0 else [1, pow(x[0], -1, r)]
         if solver == "Bits":
             v = x[0] % r
-            return [(v >> (arg - 1 - i)) & 1 if arg - 1 - i < r.bit_length() else 0 for i in range(arg)]
+            return [(v >> (arg - 1 - i)) & 1 for i in range(arg)]
         if solver == "Xor":
             return [(x[0] + x[1] - 2 * x[0] * x[1]) % r]
         if solver == "Or":
@@ -272,6 +284,10 @@ class Interpreter:
                     raise UnsatisfiedConstraint(s.error)
             elif isinstance(s, Directive):
                 xs = [self.evaluate_quad(c, w, q) for q in s.inputs]
-                for o, val in zip(s.outputs, self.execute_solver(c, s.solver, s.arg, xs)):
+                if s.solver == "Bits" and self.should_try_out_of_range and s.arg >= c.r.bit_length():
+                    res = self.try_solve_with_out_of_range_bits(c, s.arg, xs[-1])     # lib.rs:94-101
+                else:
+                    res = self.execute_solver(c, s.solver, s.arg, xs)
+                for o, val in zip(s.outputs, res):
                     w.insert(o, val)
         return w
