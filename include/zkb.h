@@ -209,6 +209,20 @@ int32_t zkb_prog_compute_witness(zkb_ctx* ctx, uint64_t prog_handle, const uint6
 int32_t zkb_prog_set_witness(zkb_ctx* ctx, uint64_t prog_handle, const uint8_t* witness_bytes, size_t len);
 int32_t zkb_prog_public_inputs(zkb_ctx* ctx, uint64_t prog_handle, uint64_t* out, uint64_t cap, uint64_t* count);
 
+/* ---- GM17 ------------------------------------------------------------------------
+ * The second proving scheme of the same trait: `impl Backend<T, GM17> for Ark` (zokrates_ark/src/gm17.rs:43-75 ->
+ * ark-gm17 0.3.0 `ProvingKey::deserialize_unchecked`, `create_proof`).  pk_bytes: ark's `serialize_unchecked` of the GM17
+ * `ProvingKey` (vk{h_g2, g_alpha_g1, h_beta_g2, g_gamma_g1, h_gamma_g2, query}, a_query, b_query, c_query_1, c_query_2,
+ * g_gamma_z, h_gamma_z, g_ab_gamma_z, g_gamma2_z2, g_gamma2_z_t).  zkb_gm17_prove: z as in zkb_groth16_prove (NULL: the resident
+ * assignment of the R1CS); d1, d2, r: the three masks `create_random_proof` draws in that order, canonical LE;
+ * proof_out = A.x | A.y | B.x.c0 | B.x.c1 | B.y.c0 | B.y.c1 | C.x | C.y like the Groth16 proof.  The R1CS -> SAP witness map, the
+ * five MSMs and the transforms run on the device with the Groth16 kernels.  ark-gm17's sources are not part of the reference
+ * tree: restated in oracle/gm17.py, parity unpinned against real ark-gm17 output. */
+int32_t zkb_gm17_pk_load(zkb_ctx* ctx, const uint8_t* pk_bytes, size_t len, uint64_t* pk_handle);
+int32_t zkb_gm17_pk_free(zkb_ctx* ctx, uint64_t pk_handle);
+int32_t zkb_gm17_prove(zkb_ctx* ctx, uint64_t pk_handle, uint64_t r1cs_handle, const uint64_t* z, const uint64_t d1[4],
+                       const uint64_t d2[4], const uint64_t r[4], uint8_t* proof_out, size_t proof_cap);
+
 /* ---- building blocks (micro-benchmarks and parity tests; BASELINE.json config 5) ---------------
  * points: ark uncompressed affine encoding (x | y, canonical LE, infinity flag 0x40 in the last
  * byte) as in proving.key; scalars canonical LE 32 bytes; out: one point in the same encoding.

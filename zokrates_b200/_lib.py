@@ -29,7 +29,7 @@ SYMBOLS = [
     "zkb_pk_table_info", "zkb_ctx_set_option", "zkb_groth16_prove_submit", "zkb_groth16_prove_collect",
     "zkb_groth16_prove_collect_partial", "zkb_groth16_prove_begin_async", "zkb_groth16_prove_end_async",
     "zkb_prog_load", "zkb_prog_info", "zkb_prog_free", "zkb_prog_compute_witness", "zkb_prog_set_witness",
-    "zkb_prog_public_inputs",
+    "zkb_prog_public_inputs", "zkb_gm17_pk_load", "zkb_gm17_pk_free", "zkb_gm17_prove",
 ]
 
 OPT_TABLES, OPT_TABLE_MIN_LOG, OPT_TABLE_C, OPT_Z_MODE, OPT_NTT_TILE_MIN, OPT_NTT_MAX_S, OPT_BITSUM_RADIX, OPT_PK_CACHE, OPT_NTT_KERNEL = 1, 2, 3, 4, 5, 6, 7, 8, 9
@@ -94,6 +94,9 @@ class Library:
         d.zkb_groth16_finalize_prepare.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         d.zkb_r1cs_check.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, _u64p]
         d.zkb_witness_eval.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, _u64p]
+        d.zkb_gm17_pk_load.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, _u64p]
+        d.zkb_gm17_pk_free.argtypes = [C.c_void_p, C.c_uint64]
+        d.zkb_gm17_prove.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         d.zkb_prog_load.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, _u64p]
         d.zkb_prog_info.argtypes = [C.c_void_p, C.c_uint64, _u64p]
         d.zkb_prog_free.argtypes = [C.c_void_p, C.c_uint64]
@@ -387,6 +390,24 @@ class Context:
         out = np.zeros((max(n.value, 1), 4), dtype=np.uint64)
         self.lib.check(self.lib.dll.zkb_prog_public_inputs(self.h, prog, out.ctypes.data, n.value, C.byref(n)))
         return fr_from_array(out[:n.value])
+
+    # -- GM17
+    def gm17_pk_load(self, pk_bytes: bytes) -> int:
+        buf = np.frombuffer(pk_bytes, dtype=np.uint8)
+        h = C.c_uint64(0)
+        self.lib.check(self.lib.dll.zkb_gm17_pk_load(self.h, buf.ctypes.data, len(buf), C.byref(h)))
+        return h.value
+
+    def gm17_pk_free(self, h: int):
+        self.lib.check(self.lib.dll.zkb_gm17_pk_free(self.h, h))
+
+    def gm17_prove(self, pk: int, r1cs: int, z, d1: int, d2: int, r: int) -> bytes:
+        zz = None if z is None else np.ascontiguousarray(z, dtype=np.uint64)
+        m = fr_array([d1, d2, r])
+        out = np.zeros(8 * self.fq_bytes, dtype=np.uint8)
+        self.lib.check(self.lib.dll.zkb_gm17_prove(self.h, pk, r1cs, None if zz is None else zz.ctypes.data, m[0].ctypes.data,
+                                                   m[1].ctypes.data, m[2].ctypes.data, out.ctypes.data, len(out)))
+        return out.tobytes()
 
     # -- building blocks
     def msm(self, group: int, points: bytes, scalars: np.ndarray) -> bytes:

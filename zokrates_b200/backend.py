@@ -143,6 +143,36 @@ class B200:
         return Proof.from_raw(c, raw, inputs)
 
     @staticmethod
+    def generate_proof_gm17(program: Prog, witness: Witness, proving_key, rng: StdRng, device: int = 0,
+                            lib: Optional[_lib.Library] = None) -> Proof:
+        """`impl Backend<T, GM17> for Ark`::generate_proof (zokrates_ark/src/gm17.rs:43-75) on the GPU: the proving key is ark-gm17's
+        `ProvingKey::serialize_unchecked`; `create_random_proof` draws d1, d2, r in that order.  Same R1CS synthesis and
+        public-input order as Groth16; the proof JSON carries scheme "gm17"."""
+        c = _curve(program.curve)
+        pk_bytes = proving_key.read() if hasattr(proving_key, "read") else bytes(proving_key)
+        inputs = program.public_inputs_values(witness)
+        d1 = fr_rand(c, rng)
+        d2 = fr_rand(c, rng)
+        r = fr_rand(c, rng)
+        r1cs = synthesize(program)
+        try:
+            z = r1cs.assignment(witness)
+        except KeyError as e:
+            raise RuntimeError(f"AssignmentMissing: {e}")
+        ctx = context(c, device, lib)
+        with ctx.lock:
+            rh = ctx.r1cs_load(r1cs.num_constraints, r1cs.num_instance, r1cs.num_witness, r1cs.matrices())
+            pkh = None
+            try:
+                pkh = ctx.gm17_pk_load(pk_bytes)
+                raw = ctx.gm17_prove(pkh, rh, z, d1, d2, r)
+            finally:
+                if pkh:
+                    ctx.gm17_pk_free(pkh)
+                ctx.r1cs_free(rh)
+        return Proof.from_raw(c, raw, inputs, scheme="gm17")
+
+    @staticmethod
     def compute_witness_files(out_bytes: bytes, inputs, curve="bn128", try_out_of_range: bool = False, device: int = 0,
                               lib: Optional[_lib.Library] = None) -> bytes:
         """`zokrates compute-witness` on the device: program file + argument values -> witness file bytes

@@ -343,6 +343,23 @@ int32_t zkb_prog_public_inputs(zkb_ctx* ctx, uint64_t h, uint64_t* out, uint64_t
     if (count) *count = n;
   });
 }
+int32_t zkb_gm17_pk_load(zkb_ctx* ctx, const uint8_t* pk_bytes, size_t len, uint64_t* h) {
+  return guard(ctx, [&] {
+    if (!pk_bytes || !h) throw Error(ZKB_E_ARG, "null argument");
+    *h = ctx->eng->gm17_pk_load(pk_bytes, len);
+  });
+}
+int32_t zkb_gm17_pk_free(zkb_ctx* ctx, uint64_t h) { return guard(ctx, [&] { ctx->eng->gm17_pk_free(h); }); }
+int32_t zkb_gm17_prove(zkb_ctx* ctx, uint64_t pk, uint64_t r1cs, const uint64_t* z, const uint64_t d1[4], const uint64_t d2[4],
+                       const uint64_t r[4], uint8_t* proof_out, size_t proof_cap) {
+  return guard(ctx, [&] {
+    if (!d1 || !d2 || !r || !proof_out) throw Error(ZKB_E_ARG, "null argument");
+    uint64_t sz[4];
+    ctx->eng->sizes(sz);
+    if (proof_cap < sz[2]) throw Error(ZKB_E_ARG, "proof buffer too small");
+    ctx->eng->gm17_prove(pk, r1cs, z, d1, d2, r, proof_out);
+  });
+}
 int32_t zkb_field_op(zkb_ctx* ctx, int32_t field, int32_t op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n) {
   return guard(ctx, [&] {
     if (!a || !out) throw Error(ZKB_E_ARG, "null argument");

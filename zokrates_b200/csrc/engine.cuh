@@ -1858,6 +1858,21 @@ class Engine : public EngineBase {
     else throw Error(ZKB_E_ARG, "field");
   }
 
+  // ------------------------------------------------------------------------------ GM17 (see gm17.cuh)
+  struct Gm17Pk {
+    uint64_t ni = 0, nv = 0, nh = 0;            // instance count (incl. one), SAP variables (incl. one), |g_gamma2_z_t|
+    DevBuf<G1A> a, c1, c2, gz;                  // a_query[1..], c_query_1, c_query_2[1..], g_gamma2_z_t
+    DevBuf<G2A> b;                              // b_query[1..]
+    HG1A h1[6];                                 // a_query[0], c_query_2[0], g_gamma_z, g_ab_gamma_z, g_gamma2_z2, g_gamma2_z_t[0]
+    HG2A h2[2];                                 // b_query[0], h_gamma_z
+  };
+  std::map<uint64_t, std::unique_ptr<Gm17Pk>> gm17_pks_;
+  uint64_t gm17_pk_load(const uint8_t* pk, size_t len) override;
+  void gm17_pk_free(uint64_t h) override { if (!gm17_pks_.erase(h)) throw Error(ZKB_E_ARG, "unknown gm17 pk handle"); }
+  template <class F, class HX> HX gm17_msm(const Fr* scalars, const Affine<F>* pts, uint64_t n, bool replan);
+  void gm17_prove(uint64_t pk, uint64_t r1cs, const uint64_t* z, const uint64_t* d1, const uint64_t* d2, const uint64_t* r,
+                  uint8_t* proof_out) override;
+
   // ------------------------------------------------------------------------------ setup (see setup.cuh)
   template <class F> void fb_build(FixedBase<F>& fb, Affine<F> stdgen, const uint32_t* gk);
   template <class F> void fb_emit(const FixedBase<F>& fb, const Fr* scalars, size_t count, uint32_t* dst);

@@ -60,6 +60,10 @@ struct EngineBase {
   virtual void prog_set_witness(uint64_t h, const uint8_t* wit, size_t len) = 0;
   virtual uint64_t prog_public_inputs(uint64_t h, uint64_t* out, uint64_t cap) = 0;
   virtual void field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n) = 0;
+  virtual uint64_t gm17_pk_load(const uint8_t* pk, size_t len) = 0;
+  virtual void gm17_pk_free(uint64_t h) = 0;
+  virtual void gm17_prove(uint64_t pk, uint64_t r1cs, const uint64_t* z, const uint64_t* d1, const uint64_t* d2, const uint64_t* r,
+                          uint8_t* proof_out) = 0;
   virtual size_t setup_size(uint64_t r1cs) = 0;
   virtual void setup(uint64_t r1cs, const uint64_t* trapdoor7, uint8_t* pk_out, size_t cap, size_t* len) = 0;
   std::vector<std::pair<const char*, double>> timings;

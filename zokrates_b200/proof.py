@@ -61,16 +61,17 @@ class Proof:
     proof: ProofPoints
     inputs: List[str]
     curve: str = "bn128"
+    scheme: str = SCHEME_NAME      # "g16" (scheme/groth16.rs) or "gm17" (scheme/gm17.rs:31): same a / b / c point layout
 
     @classmethod
-    def from_raw(cls, c: Curve, raw: bytes, inputs: List[int]) -> "Proof":
+    def from_raw(cls, c: Curve, raw: bytes, inputs: List[int], scheme: str = SCHEME_NAME) -> "Proof":
         """raw = A.x|A.y|B.x.c0|B.x.c1|B.y.c0|B.y.c1|C.x|C.y canonical LE (zkb_groth16_prove output)."""
         n = c.fq_bytes
         if len(raw) != 8 * n:
             raise ValueError("bad proof length")
         f = [_hex(raw[i * n:(i + 1) * n]) for i in range(8)]
         pts = ProofPoints(G1Affine(f[0], f[1]), G2Affine((f[2], f[3]), (f[4], f[5])), G1Affine(f[6], f[7]))
-        return cls(pts, [_hex(int(v).to_bytes(c.fr_bytes, "little")) for v in inputs], c.name)
+        return cls(pts, [_hex(int(v).to_bytes(c.fr_bytes, "little")) for v in inputs], c.name, scheme)
 
     def to_raw(self) -> bytes:
         c = _curve(self.curve)
@@ -84,7 +85,7 @@ class Proof:
     def to_tagged_json(self) -> str:
         """`serde_json::to_string_pretty(&TaggedProof::<T, S>::new(proof.proof, proof.inputs))`
         (zokrates_cli/src/ops/generate_proof.rs:188-194): keys scheme, curve, proof, inputs."""
-        return json.dumps({"scheme": SCHEME_NAME, "curve": self.curve, "proof": self.proof.to_json(),
+        return json.dumps({"scheme": self.scheme, "curve": self.curve, "proof": self.proof.to_json(),
                            "inputs": self.inputs}, indent=2)
 
     @classmethod
@@ -92,7 +93,7 @@ class Proof:
         d = json.loads(text)
         p = d["proof"]
         pts = ProofPoints(G1Affine(*p["a"]), G2Affine(tuple(p["b"][0]), tuple(p["b"][1])), G1Affine(*p["c"]))
-        return cls(pts, list(d["inputs"]), d.get("curve", "bn128"))
+        return cls(pts, list(d["inputs"]), d.get("curve", "bn128"), d.get("scheme", SCHEME_NAME))
 
 
 @dataclass
@@ -106,7 +107,7 @@ class VerificationKey:
 
     def to_tagged_json(self) -> str:
         """TaggedVerificationKey: scheme, curve, then the flattened vk (tagged.rs:7-13)."""
-        return json.dumps({"scheme": SCHEME_NAME, "curve": self.curve, "alpha": self.alpha.to_json(),
+        return json.dumps({"scheme": self.scheme, "curve": self.curve, "alpha": self.alpha.to_json(),
                            "beta": self.beta.to_json(), "gamma": self.gamma.to_json(), "delta": self.delta.to_json(),
                            "gamma_abc": [g.to_json() for g in self.gamma_abc]}, indent=2)
 
