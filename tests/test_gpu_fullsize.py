@@ -142,8 +142,10 @@ def test_table_fallback_when_hbm_is_short(gpu_lib, oracle_c):
     reported 'no-memory' (the h table, 5x smaller, still fits), the proof is unchanged, and ZKB_OPT_TABLES = 2 turns the
     same situation into ZKB_E_OOM."""
     import torch
+    from zokrates_b200._lib import OPT_PK_CACHE
     circ = Circuit(gpu_lib, 0, BN254, 18, "uniform")
     ctx, c = circ.ctx, circ.c
+    ctx.set_option(OPT_PK_CACHE, 0)            # every load must build (or fail to build) its own tables here
     expected = oracle_c.trapdoor_expected(0, circ.r1, TD, circ.z, R, S, c.fq_bytes)
     pkh = ctx.pk_load(circ.pk)
     full_info = ctx.pk_table_info(pkh)
@@ -171,6 +173,7 @@ def test_table_fallback_when_hbm_is_short(gpu_lib, oracle_c):
         del hog
         torch.cuda.empty_cache()
         ctx.set_option(OPT_TABLES, 1)
+        ctx.set_option(OPT_PK_CACHE, 1)
     circ.close()
 
 
@@ -210,3 +213,36 @@ def test_standalone_msm_vs_c_oracle_large(gpu_lib, oracle_c, cid, c):
         n = 1 << 16
         assert ctx.msm(2, b2[:n * g2b], scalars[:n]) == oracle_c.msm(cid, 2, b2[:n * g2b], scalars[:n], c.fq_bytes)
     ctx.close()
+
+
+def test_pk_cache_by_content(gpu_lib, oracle_c):
+    """ZKB_OPT_PK_CACHE: the trait-shaped pk_load / prove / pk_free per proof builds the window tables once — a second load of the
+    same bytes returns a handle onto the resident key (also after the last handle was released), other bytes or other table
+    options do not hit; proofs are unchanged."""
+    import time
+    circ = Circuit(gpu_lib, 0, BN254, 16, "uniform")
+    ctx, c = circ.ctx, circ.c
+    expected = oracle_c.trapdoor_expected(0, circ.r1, TD, circ.z, R, S, c.fq_bytes)
+    t = time.perf_counter(); h1 = ctx.pk_load(circ.pk); cold = time.perf_counter() - t
+    assert "pk_cache_hit" not in ctx.timings()
+    h2 = ctx.pk_load(circ.pk)
+    assert h2 != h1 and "pk_cache_hit" in ctx.timings()
+    assert ctx.prove(h2, circ.h, circ.z, R, S) == expected
+    ctx.pk_free(h1); ctx.pk_free(h2)
+    with pytest.raises(ZkbError):
+        ctx.pk_table_info(h2)
+    t = time.perf_counter(); h3 = ctx.pk_load(circ.pk); warm = time.perf_counter() - t
+    assert "pk_cache_hit" in ctx.timings() and warm < cold
+    assert ctx.prove(h3, circ.h, circ.z, R, S) == expected
+    ctx.pk_free(h3)
+    other = bytearray(circ.pk); other[100] ^= 1                      # different bytes (a coordinate of beta_g2): a miss
+    h4 = ctx.pk_load(bytes(other))
+    assert "pk_cache_hit" not in ctx.timings()
+    ctx.pk_free(h4)
+    ctx.set_option(OPT_TABLES, 0)
+    h5 = ctx.pk_load(circ.pk)                                          # other table options: a miss, no tables
+    assert "pk_cache_hit" not in ctx.timings() and ctx.pk_table_info(h5)["z_tables"] == "disabled"
+    assert ctx.prove(h5, circ.h, circ.z, R, S) == expected
+    ctx.pk_free(h5)
+    ctx.set_option(OPT_TABLES, 1)
+    circ.close()

@@ -15,6 +15,7 @@
 #include <future>
 #include "fp64.cuh"
 #include "msm.cuh"
+#include "msm_affine.cuh"
 #include "ntt.cuh"
 #include "ntt_tile.cuh"
 #include "solvers.cuh"
@@ -32,7 +33,7 @@ struct k_fr_convert; struct k_spmv; struct k_ntt_dif; struct k_ntt_dit; struct k
 struct k_ntt_table; struct k_qap_pointwise; struct k_msm_digits; struct k_msm_scatter; struct k_msm_accum1;
 struct k_msm_accum2; struct k_msm_bitsum; struct k_pk_convert; struct k_final_a; struct k_final_b;
 struct k_final_c; struct k_final_d; struct k_point_out; struct k_field_op; struct k_setup_scalars; struct k_fixed_base;
-struct k_to_affine; struct k_copy; struct k_msm_view; struct k_solver_level; struct k_msm_table; struct k_ntt_dif_tile; struct k_ntt_dit_tile; struct k_witness_level;
+struct k_to_affine; struct k_copy; struct k_msm_view; struct k_solver_level; struct k_ba_halve; struct k_ba_round; struct k_msm_table; struct k_ntt_dif_tile; struct k_ntt_dit_tile; struct k_witness_level;
 
 // ---------------------------------------------------------------------------------------------
 // stage timer: CUDA events on the engine stream (no-op in the host emulation)
@@ -603,6 +604,7 @@ class Engine : public EngineBase {
     Event acc_done, tail_done;
     bool has_stream = false;
     // filled by msm_tail: the bit-sum reduction consumed `tree_bits` index bits and left `tree_cnt` block totals per window
+    uint32_t nt1 = 0;         // chunks of the last accumulation into this workspace (the partial lists hold 2 nt1 entries)
     uint32_t tree_cnt = 1, tree_bits = 0;
     size_t out_entries = 0;   // XYZZ entries of the result slot the host has to read: (1 + tree_bits) * W * tree_cnt
     void destroy() { if (has_stream) { stream_destroy(tail); has_stream = false; } acc_done.destroy(); tail_done.destroy(); }
@@ -1022,7 +1024,13 @@ class Engine : public EngineBase {
     if (has_wm_stream_) stream_destroy(wm_stream_);
   }
 
+  // scratch of the batch-affine rounds: shared by all MSMs (the accumulations run one after the other on the main stream)
+  DevBuf<uint8_t> ba_pts_[2];
+  DevBuf<uint32_t> ba_off_[2], ba_cnt_, ba_scan_tmp_;
+
   // phase 1 (main stream): bucket accumulation of one MSM.  Throughput-bound (INT32 multiply pipe).
+  //   optional batch-affine rounds (msm_affine.cuh): every round halves each bucket with affine additions that share one
+  //   inversion per block, then the XYZZ chunk accumulation runs on the shortened list.
   template <class F>
   void msm_accumulate(const MsmPlan& pl, const Affine<F>* pts, MsmWs& ws, StageTimer* tm, const char* accum_name, uint32_t view) {
     typedef XYZZ<F> X;
@@ -1030,19 +1038,66 @@ class Engine : public EngineBase {
     const uint32_t NB = pl.nbuckets;
     ws.buckets.ensure((size_t)NB * sizeof(X));
     X* buckets = (X*)ws.buckets.p;
-    const uint32_t nt1 = pl.nt1, T1 = pl.T1;
-    for (int k = 0; k < 2; k++) { ws.key[k].ensure(2 * (size_t)nt1 + 2); ws.val[k].ensure((2 * (size_t)nt1 + 2) * sizeof(X)); }
-    ws.tail_done.wait(st_);  // the previous proof's tail may still be reading these buffers
-    dev_zero(st_, buckets, (size_t)NB * sizeof(X));
     const uint32_t* of = pl.offsets.p + (size_t)view * (NB + 1);
     const uint32_t* so = pl.sorted.p + (size_t)view * pl.sh.n * pl.sh.W;
-    uint32_t* k0 = ws.key[0].p; X* v0 = (X*)ws.val[0].p;
+    uint64_t bound = (uint64_t)pl.sh.n * pl.sh.W;          // upper bound of the list length (the exact length is offsets[NB], on the device)
+    uint32_t rounds = 0;
+    if (opts.batch_affine > 0 && bound >= ((uint64_t)1 << opts.batch_affine_min_log) && bound < (1ull << 31)) rounds = (uint32_t)opts.batch_affine;
+    ws.tail_done.wait(st_);  // the previous proof's tail may still be reading these buffers
     if (tm && accum_name) tm->begin(accum_name);
+    const Affine<F>* cur_pts = pts;
+    for (uint32_t r = 0; r < rounds; r++) {
+      const uint64_t out_bound = (bound + NB) / 2 + 1;     // sum of ceil(L / 2) over at most NB non-empty buckets
+      ba_cnt_.ensure(NB); ba_off_[r & 1].ensure((size_t)NB + 1); ba_scan_tmp_.ensure(2 * ((size_t)NB / 2048 + 4));
+      ba_pts_[r & 1].ensure(out_bound * sizeof(Affine<F>));
+      const uint32_t* off_in = of;
+      uint32_t* cnt = ba_cnt_.p; uint32_t* off_out = ba_off_[r & 1].p;
+      launch<k_ba_halve>(st_, NB, ZKB_LAMBDA(size_t t) { ba_halve_counts_body(NB, off_in, cnt, (uint32_t)t); });
+      exclusive_scan(st_, cnt, off_out, NB, ba_scan_tmp_.p);
+      Affine<F>* out = (Affine<F>*)ba_pts_[r & 1].p;
+      const uint32_t* srt = so;
+      const Affine<F>* pin = cur_pts;
+#if !defined(ZKB_EMU)
+      {
+        constexpr int MINB = sizeof(F) > sizeof(Fq) ? 2 : 3;
+        static bool configured = false;                    // per instantiation: opt in to the dynamic shared memory size once
+        if (!configured) {
+          ZKB_CUDA(cudaFuncSetAttribute(zkb_batch_affine<F, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba_smem_bytes<F>()));
+          configured = true;
+        }
+        const size_t blocks = (size_t)((out_bound + BA_TILE - 1) / BA_TILE);
+        launch_counter()++;
+        zkb_batch_affine<F, MINB><<<(unsigned)blocks, BA_BLOCK, ba_smem_bytes<F>(), st_.s>>>(NB, off_in, off_out, srt, pin, out);
+        ZKB_CUDA(cudaGetLastError());
+      }
+#else
+      {  // the same passes as the device kernel, block after block
+        const size_t blocks = (size_t)((out_bound + BA_TILE - 1) / BA_TILE);
+        launch_counter()++;
+        for (size_t blk = 0; blk < blocks; blk++) ba_block_emulate<F>(NB, off_in, off_out, srt, pin, out, (uint32_t)blk);
+      }
+#endif
+      of = off_out; so = nullptr; cur_pts = out; bound = out_bound;
+    }
+    // chunk size of the XYZZ stage: several waves of resident threads, 8 .. 64 entries per chunk
+    uint32_t T1 = pl.T1, nt1 = pl.nt1;
+    if (rounds) {
+      uint64_t T = (bound + 600000 - 1) / 600000;
+      if (T < 8) T = 8;
+      if (T > 64) T = 64;
+      T1 = (uint32_t)((T + 1) & ~1ull);
+      nt1 = (uint32_t)((bound + T1 - 1) / T1);
+    }
+    ws.nt1 = nt1;
+    for (int k = 0; k < 2; k++) { ws.key[k].ensure(2 * (size_t)nt1 + 2); ws.val[k].ensure((2 * (size_t)nt1 + 2) * sizeof(X)); }
+    dev_zero(st_, buckets, (size_t)NB * sizeof(X));
+    uint32_t* k0 = ws.key[0].p; X* v0 = (X*)ws.val[0].p;
+    const Affine<F>* fin_pts = cur_pts;
     // G2 (Fq2 coordinates) wants > 200 registers: two blocks per SM (3 and 4 were measured equal, profiles/r01_tuning_log.md)
     if (sizeof(F) > sizeof(Fq)) {
-      launch<k_msm_accum1, 128, ZKB_G2_MINB>(st_, nt1, ZKB_LAMBDA(size_t t) { msm_accum1_body<F>(NB, T1, of, so, pts, buckets, k0, v0, nt1, (uint32_t)t); });
+      launch<k_msm_accum1, 128, ZKB_G2_MINB>(st_, nt1, ZKB_LAMBDA(size_t t) { msm_accum1_body<F>(NB, T1, of, so, fin_pts, buckets, k0, v0, nt1, (uint32_t)t); });
     } else {
-      launch<k_msm_accum1>(st_, nt1, ZKB_LAMBDA(size_t t) { msm_accum1_body<F>(NB, T1, of, so, pts, buckets, k0, v0, nt1, (uint32_t)t); });
+      launch<k_msm_accum1>(st_, nt1, ZKB_LAMBDA(size_t t) { msm_accum1_body<F>(NB, T1, of, so, fin_pts, buckets, k0, v0, nt1, (uint32_t)t); });
     }
     if (tm && accum_name) tm->end();
     ws.acc_done.record(st_);
@@ -1057,7 +1112,7 @@ class Engine : public EngineBase {
     Stream ts = tail_stream(ws);
     ws.acc_done.wait(ts);
     size_t span = (tm && tail_name) ? tm->begin_on(ts, tail_name) : 0;
-    const uint32_t W = pl.sh.pre ? 1 : pl.sh.W, B = pl.sh.B, T2 = pl.T2, nt1 = pl.nt1;
+    const uint32_t W = pl.sh.pre ? 1 : pl.sh.W, B = pl.sh.B, T2 = pl.T2, nt1 = ws.nt1;   // chunks of THIS accumulation
     X* buckets = (X*)ws.buckets.p;
     uint32_t L = 2 * nt1;
     int cur = 0;

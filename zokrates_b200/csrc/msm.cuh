@@ -154,14 +154,15 @@ ZKB_HDN inline void msm_accum1_body(uint32_t nbuckets, uint32_t T, const uint32_
     // software pipeline: the index (and, when registers allow, the point) of entry p+1 is fetched before the
     // mixed addition of entry p, so the dependent gather sorted[p] -> points[.] hides behind ~2500 instructions
     constexpr bool PREFETCH_POINT = sizeof(Affine<F>) <= 64;
-    uint32_t e = sorted[pos];
+    // sorted == nullptr: the points ARE the list (output of the batch-affine rounds, msm_affine.cuh), entry p = point p
+    uint32_t e = sorted ? sorted[pos] : pos;
     Affine<F> q;
     if (PREFETCH_POINT) q = points[e & ~MSM_NEG];
     for (uint32_t p = pos; p < end; p++) {
       uint32_t e_next = 0;
       Affine<F> q_next;
       if (p + 1 < end) {
-        e_next = sorted[p + 1];
+        e_next = sorted ? sorted[p + 1] : p + 1;
         if (PREFETCH_POINT) q_next = points[e_next & ~MSM_NEG];
       }
       if (p == bend) {

@@ -14,7 +14,7 @@
 //     extra multiplication per element and pass replace S/2 gathered loads per element.  Exact field arithmetic: same bits.
 //   * ASYNCHRONOUS tile load: global -> shared with cp.async (LDGSTS), no register staging.
 //   * CONFLICT-FREE shared memory: an element is split into two 16-byte halves stored in two planes (a quarter-warp of
-//     LDS.128 then covers all 32 banks), positions padded by one slot per 8 (strided register steps hit distinct banks).
+//     LDS.128 then covers all 32 banks), slots XOR-swizzled inside rows of 8 (strided register steps hit distinct banks).
 //   The last compute phase writes its registers straight to global memory (no store phase).
 #pragma once
 #include "ntt.cuh"
@@ -23,10 +23,25 @@
 #if !defined(ZKB_EMU)
 namespace zkb {
 
-static constexpr uint32_t NTT2_PLANE = NTT_TILE + NTT_TILE / 8;      // padded slots per plane
-static constexpr uint32_t NTT2_SMEM = (2 * NTT2_PLANE + 2 * 512) * 16;  // data planes + twiddle planes: 53 248 bytes
+static constexpr uint32_t NTT2_PLANE = NTT_TILE;                     // slots per plane (swizzled inside rows of 8, no padding)
+static constexpr uint32_t NTT2_SMEM = (2 * NTT2_PLANE + 2 * 512) * 16;  // data planes + twiddle planes: 49 152 bytes
 
-__device__ __forceinline__ uint32_t ntt2_slot(uint32_t pos) { return pos + (pos >> 3); }
+// A quarter-warp of LDS.128 / STS.128 is conflict-free when its 8 slots differ modulo 8 (8 x 16 B = all 32 banks).  The register
+// steps address 8 slots whose indices differ in three bits: {0,1,2} (half-span >= 8), {0,1,4}, {0,1,5}, {0,3,4}, {0,4,5},
+// {2,3,4} or {3,4,5} depending on the step.  XOR-ing the low three bits with a GF(2)-linear image of bits 3, 4, 5
+// (010, 101, 110) makes every one of these triples independent, so every step is conflict-free; the map is a bijection
+// inside each row of 8 slots.
+__device__ __forceinline__ uint32_t ntt2_slot(uint32_t pos) {
+  const uint32_t x = ((pos >> 3) & 1u) * 2u ^ ((pos >> 4) & 1u) * 5u ^ ((pos >> 5) & 1u) * 6u;
+  return pos ^ x;
+}
+// The twiddle index of a butterfly is imod << sh: 8 lanes read entries whose indices differ in bits {sh, sh+1, sh+2}.  Images
+// 011, 110, 111, 101, 001, 010 for bits 3..8 keep any three consecutive bits independent.
+__device__ __forceinline__ uint32_t ntt2_wslot(uint32_t wi) {
+  const uint32_t x = ((wi >> 3) & 1u) * 3u ^ ((wi >> 4) & 1u) * 6u ^ ((wi >> 5) & 1u) * 7u ^ ((wi >> 6) & 1u) * 5u ^ ((wi >> 7) & 1u) * 1u ^
+                     ((wi >> 8) & 1u) * 2u;
+  return wi ^ x;
+}
 
 template <class Fr>
 __device__ __forceinline__ Fr ntt2_ld(const uint4* lo, const uint4* hi, uint32_t slot) {
@@ -116,14 +131,14 @@ __device__ __forceinline__ void ntt2_stages(Fr* __restrict__ x, const Fr* __rest
         const uint32_t wi = imod << (9 - lg_hl);                   // index into the 512 roots W_1024^k
         Fr u = e[m];
         if (DIT) {
-          Fr v = wi ? Fr::mul(e[m + hm], ntt2_ld<Fr>(wlo, whi, wi)) : e[m + hm];
+          Fr v = wi ? Fr::mul(e[m + hm], ntt2_ld<Fr>(wlo, whi, ntt2_wslot(wi))) : e[m + hm];
           e[m] = Fr::add(u, v);
           e[m + hm] = Fr::sub(u, v);
         } else {
           Fr v = e[m + hm];
           e[m] = Fr::add(u, v);
           Fr d = Fr::sub(u, v);
-          e[m + hm] = wi ? Fr::mul(d, ntt2_ld<Fr>(wlo, whi, wi)) : d;
+          e[m + hm] = wi ? Fr::mul(d, ntt2_ld<Fr>(wlo, whi, ntt2_wslot(wi))) : d;
         }
       }
     }
@@ -157,8 +172,8 @@ __global__ void __launch_bounds__(NTT_BLOCK, 4) zkb_ntt_tile2(Fr* x, const Fr* t
     const uint32_t stride = 1u << (ps.log_n - NTT_TILE_LOG);
     for (uint32_t k = threadIdx.x; k < 512; k += NTT_BLOCK) {
       const uint4* src = (const uint4*)(tw + (size_t)k * stride);
-      wlo[k] = src[0];
-      whi[k] = src[1];
+      wlo[ntt2_wslot(k)] = src[0];
+      whi[ntt2_wslot(k)] = src[1];
     }
   }
   for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
