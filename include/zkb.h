@@ -88,7 +88,9 @@ int32_t zkb_pk_table_info(zkb_ctx* ctx, uint64_t pk_handle, uint64_t out[8]);
 #define ZKB_OPT_NTT_MAX_S 6     /* stage bits per tile pass, 1..10; default 10 */
 #define ZKB_OPT_BITSUM_RADIX 7  /* bucket reduction by bit sums: levels of radix 2 (default) or 8 */
 #define ZKB_OPT_BATCH_AFFINE 10 /* rounds of pairwise AFFINE additions inside the buckets (one shared inversion per block, 6 instead of
-                                 * 10 multiplications per addition) in front of the XYZZ bucket accumulation; default 3, 0 = off */
+                                 * 10 multiplications per addition) in front of the XYZZ bucket accumulation; default 0 = off: the
+                                 * one serial inversion per block makes it 3.3x slower than the direct path on B200 as implemented
+                                 * (profiles/r02_batch_affine.md); kept as a tested experimental path */
 #define ZKB_OPT_BATCH_AFFINE_MIN_LOG 11 /* smallest sorted list (log2 entries) that gets the affine rounds; default 16 */
 #define ZKB_OPT_NTT_KERNEL 9    /* tile pass of the NTT: 2 (default) four-step twiddles + cp.async tile load, 1 the round-1 pass */
 #define ZKB_OPT_PK_CACHE 8      /* 1 (default): zkb_pk_load of bytes that are already resident returns a handle onto the same key

@@ -122,7 +122,7 @@ def test_batch_affine_large_gpu(cid, gpu_lib, oracle_c):
             small = rs.rand(n) < 0.9
             sc[small, 1:] = 0
             sc[small, 0] = rs.randint(0, 2, size=int(small.sum())).astype(np.uint64)
-        want = oracle_c.msm(cid, 1, pts, sc, 32)
+        want = oracle_c.msm(cid, 1, pts, sc, c.fq_bytes)
         for rounds in (0, 3):
             ctx.set_option(OPT_BATCH_AFFINE, rounds)
             ctx.set_option(OPT_BATCH_AFFINE_MIN_LOG, 0)

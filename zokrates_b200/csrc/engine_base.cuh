@@ -15,7 +15,8 @@ struct Options {
   int64_t z_mode = 0;         // ZKB_OPT_Z_MODE: 0 sample the assignment, 1 always the shared-bucket table mode, 2 always per-window buckets
   int64_t ntt_tile_min = 10;  // ZKB_OPT_NTT_TILE_MIN: transforms of 2^k points and more use the shared-memory tile passes
   int64_t ntt_max_s = 10;     // ZKB_OPT_NTT_MAX_S: stage bits per tile pass
-  int64_t batch_affine = 3;   // ZKB_OPT_BATCH_AFFINE: rounds of pairwise affine additions (shared inversion) before the XYZZ accumulation; 0 = off
+  int64_t batch_affine = 0;   // ZKB_OPT_BATCH_AFFINE: rounds of pairwise affine additions (shared inversion) before the XYZZ accumulation; 0 = off
+                              // (default: measured 3.3x SLOWER than the direct path on B200, profiles/r02_batch_affine.md)
   int64_t batch_affine_min_log = 16;   // ZKB_OPT_BATCH_AFFINE_MIN_LOG: only for lists of 2^k (pair, window) entries and more
   int64_t ntt_kernel = 2;     // ZKB_OPT_NTT_KERNEL: 2 = four-step twiddles / cp.async tile load (ntt_tile.cuh), 1 = the round-1 tile pass
   int64_t pk_cache = 1;       // ZKB_OPT_PK_CACHE: share proving keys by content and keep the last released one resident

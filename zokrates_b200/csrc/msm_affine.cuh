@@ -1,4 +1,10 @@
-// Batch-affine rounds in front of the bucket accumulation.
+// Batch-affine rounds in front of the bucket accumulation.  EXPERIMENTAL, OFF BY DEFAULT (ZKB_OPT_BATCH_AFFINE = 0): measured on
+// B200 the rounds are 3.3x slower than the direct XYZZ path (2^20 points: 5.2 + 2.4 + 1.3 + 0.3 ms against 2.5 ms) — the single
+// Fermat inversion per block (~380 dependent multiplications on one thread, ~0.1 ms) stalls 127 threads, and with four blocks
+// per SM the stalls do not interleave; a three-kernel split (products / parallel inversions / additions) would remove the stall
+// but at 7.4 multiplications per addition with two passes over the points it lands at parity with the direct path at best
+// (profiles/r02_batch_affine.md).  Kept because it is correct, tested (tests/test_batch_affine.py) and the starting point for that
+// split.
 //
 // The mixed addition into an XYZZ accumulator costs 10 field multiplications (8M + 2S; 28 base-field multiplications in
 // G2).  Adding two AFFINE points costs 1 inversion + 2M + 1S, and Montgomery's trick turns k inversions into one inversion
