@@ -171,6 +171,13 @@ int32_t zkb_groth16_prove_collect_partial(zkb_ctx* ctx, uint64_t ticket, uint8_t
 int32_t zkb_groth16_prove_begin_async(zkb_ctx* ctx, uint64_t pk_handle, uint64_t r1cs_handle, const uint64_t* z,
                                       uint32_t chain_mask, void* chain_dev_ptrs[3], uint64_t* chain_bytes, uint64_t* ticket);
 int32_t zkb_groth16_prove_end_async(zkb_ctx* ctx, uint64_t ticket);
+/* Stream-ordered chain exchange: with ZKB_CHAIN_NO_HOST_SYNC or-ed into chain_mask, begin_async returns without waiting for this
+ * rank's chains; `chains_to_stream` makes `cuda_stream` (a cudaStream_t: the stream the caller's NCCL broadcasts are ordered on)
+ * wait for them, and `stream_to_finish` makes the finish step (end_async) wait for everything enqueued on `cuda_stream` so far —
+ * the host never blocks between two proofs. */
+#define ZKB_CHAIN_NO_HOST_SYNC 0x80000000u
+int32_t zkb_groth16_prove_chains_to_stream(zkb_ctx* ctx, uint64_t ticket, void* cuda_stream);
+int32_t zkb_groth16_prove_stream_to_finish(zkb_ctx* ctx, uint64_t ticket, void* cuda_stream);
 
 /* ---- witness side -------------------------------------------------
  * zkb_r1cs_check: (A z) o (B z) == C z for every constraint, on the device; z = NULL checks the resident assignment.

@@ -28,6 +28,7 @@ SYMBOLS = [
     "zkb_groth16_prove_end", "zkb_groth16_finalize_prepare", "zkb_r1cs_check", "zkb_witness_eval",
     "zkb_pk_table_info", "zkb_ctx_set_option", "zkb_groth16_prove_submit", "zkb_groth16_prove_collect",
     "zkb_groth16_prove_collect_partial", "zkb_groth16_prove_begin_async", "zkb_groth16_prove_end_async",
+    "zkb_groth16_prove_chains_to_stream", "zkb_groth16_prove_stream_to_finish",
     "zkb_prog_load", "zkb_prog_info", "zkb_prog_free", "zkb_prog_compute_witness", "zkb_prog_set_witness",
     "zkb_prog_public_inputs", "zkb_gm17_pk_load", "zkb_gm17_pk_free", "zkb_gm17_prove",
 ]
@@ -91,6 +92,8 @@ class Library:
         d.zkb_groth16_prove_begin_async.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32,
                                                     C.POINTER(C.c_void_p), _u64p, _u64p]
         d.zkb_groth16_prove_end_async.argtypes = [C.c_void_p, C.c_uint64]
+        d.zkb_groth16_prove_chains_to_stream.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        d.zkb_groth16_prove_stream_to_finish.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         d.zkb_groth16_finalize_prepare.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         d.zkb_r1cs_check.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, _u64p]
         d.zkb_witness_eval.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, _u64p]
@@ -306,6 +309,12 @@ class Context:
         t = C.c_uint64(0)
         self.lib.check(self.lib.dll.zkb_groth16_prove_begin_async(self.h, pk, r1cs, zp, chain_mask, ptrs, C.byref(nbytes), C.byref(t)))
         return int(t.value), [int(p or 0) for p in ptrs], int(nbytes.value)
+
+    def prove_chains_to_stream(self, ticket: int, cuda_stream: int):
+        self.lib.check(self.lib.dll.zkb_groth16_prove_chains_to_stream(self.h, ticket, C.c_void_p(cuda_stream)))
+
+    def prove_stream_to_finish(self, ticket: int, cuda_stream: int):
+        self.lib.check(self.lib.dll.zkb_groth16_prove_stream_to_finish(self.h, ticket, C.c_void_p(cuda_stream)))
 
     def prove_end_async(self, ticket: int):
         self.lib.check(self.lib.dll.zkb_groth16_prove_end_async(self.h, ticket))

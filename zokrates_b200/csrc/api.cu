@@ -239,6 +239,12 @@ int32_t zkb_groth16_prove_begin_async(zkb_ctx* ctx, uint64_t pk, uint64_t r1cs, 
     *ticket = ctx->eng->prove_begin_async(pk, r1cs, z, chain_mask, chain_dev_ptrs, chain_bytes);
   });
 }
+int32_t zkb_groth16_prove_chains_to_stream(zkb_ctx* ctx, uint64_t ticket, void* cuda_stream) {
+  return guard(ctx, [&] { ctx->eng->prove_chains_to_stream(ticket, cuda_stream); });
+}
+int32_t zkb_groth16_prove_stream_to_finish(zkb_ctx* ctx, uint64_t ticket, void* cuda_stream) {
+  return guard(ctx, [&] { ctx->eng->prove_stream_to_finish(ticket, cuda_stream); });
+}
 int32_t zkb_groth16_prove_end_async(zkb_ctx* ctx, uint64_t ticket) {
   return guard(ctx, [&] { ctx->eng->prove_end_async(ticket); });
 }

@@ -618,7 +618,7 @@ class Engine : public EngineBase {
     DevBuf<uint8_t> d_win;                    // result slots of the five MSMs
     HostBuf hw;                               // pinned landing zone of the same
     std::unique_ptr<StageTimer> tm, tm2;
-    Event ev_z_ready, ev_h_ready, ev_chains_done, done;
+    Event ev_z_ready, ev_h_ready, ev_chains_done, ev_exchange, done;
     Stream fin; bool has_fin = false;         // waits for the five tails and copies the results out, off the main stream
     uint64_t pk = 0, r1cs = 0, ticket = 0;
     int state = 0;                            // 0 free, 1 begun (assignment MSMs enqueued), 2 fully enqueued (collectable)
@@ -627,7 +627,7 @@ class Engine : public EngineBase {
     std::future<FixedMults> fm;
     void destroy() {
       for (auto& w : ws) w.destroy();
-      ev_z_ready.destroy(); ev_h_ready.destroy(); ev_chains_done.destroy(); done.destroy();
+      ev_z_ready.destroy(); ev_h_ready.destroy(); ev_chains_done.destroy(); ev_exchange.destroy(); done.destroy();
       if (has_fin) { stream_destroy(fin); has_fin = false; }
     }
   };
@@ -1541,7 +1541,10 @@ class Engine : public EngineBase {
     return sl.fin;
   }
 
-  uint64_t slot_begin(uint64_t pkh, uint64_t rh, const uint64_t* z, uint32_t chain_mask) {
+  static constexpr uint32_t CHAIN_NO_HOST_SYNC = 0x80000000u;   // chain_mask flag: the caller orders the exchange with stream events
+  uint64_t slot_begin(uint64_t pkh, uint64_t rh, const uint64_t* z, uint32_t chain_mask_in) {
+    const bool no_host_sync = (chain_mask_in & CHAIN_NO_HOST_SYNC) != 0;
+    const uint32_t chain_mask = chain_mask_in & ~CHAIN_NO_HOST_SYNC;
     Pk& pk = get_pk(pkh);
     R1cs& r = get_r1cs(rh);
     const size_t n = (size_t)1 << r.log_n;
@@ -1593,7 +1596,7 @@ class Engine : public EngineBase {
     msm_exec<Fq>(sl.plan_z, pk.b1.p, w_b1, sl.ws[3], &tm, "accum1_g1_b1", 2, "tail_g1_b1");
     sl.pk = pkh; sl.r1cs = rh; sl.ticket = next_ticket_++; sl.state = 1; sl.has_rs = false;
     // chains left to other ranks: the caller exchanges buffers next, so this rank's chains must be complete in memory
-    if (chain_mask != 7) stream_sync(wm_stream_);
+    if (chain_mask != 7 && !no_host_sync) stream_sync(wm_stream_);
     return sl.ticket;
   }
 
@@ -1700,6 +1703,28 @@ class Engine : public EngineBase {
     if (chain_ptrs) { chain_ptrs[0] = sl.a.p; chain_ptrs[1] = sl.b.p; chain_ptrs[2] = sl.c.p; }
     if (chain_bytes) *chain_bytes = ((size_t)1 << get_r1cs(rh).log_n) * FRB;
     return t;
+  }
+  // Stream-ordered chain exchange (no host synchronisation): the caller's stream (NCCL / torch) waits for this rank's chains,
+  // runs its broadcasts, and the finish step waits for whatever that stream has enqueued by then.
+  void prove_chains_to_stream(uint64_t ticket, void* ext_stream) override {
+#if !defined(ZKB_EMU)
+    ProofSlot& sl = slot_of(ticket);
+    Stream ext; ext.s = (cudaStream_t)ext_stream;
+    sl.ev_chains_done.wait(ext);
+#else
+    (void)ticket; (void)ext_stream;
+#endif
+  }
+  void prove_stream_to_finish(uint64_t ticket, void* ext_stream) override {
+#if !defined(ZKB_EMU)
+    ProofSlot& sl = slot_of(ticket);
+    Stream ext; ext.s = (cudaStream_t)ext_stream;
+    if (!has_wm_stream_) throw Error(ZKB_E_INTERNAL, "no witness-map stream");
+    sl.ev_exchange.record(ext);
+    sl.ev_exchange.wait(wm_stream_);
+#else
+    (void)ticket; (void)ext_stream;
+#endif
   }
   void prove_end_async(uint64_t ticket) override {
     ProofSlot& sl = slot_of(ticket);

@@ -42,6 +42,8 @@ struct EngineBase {
   virtual uint64_t prove_begin_async(uint64_t pk, uint64_t r1cs, const uint64_t* z, uint32_t chain_mask, void* chain_ptrs[3],
                                      uint64_t* chain_bytes) = 0;
   virtual void prove_end_async(uint64_t ticket) = 0;
+  virtual void prove_chains_to_stream(uint64_t ticket, void* ext_stream) = 0;
+  virtual void prove_stream_to_finish(uint64_t ticket, void* ext_stream) = 0;
   virtual uint64_t prove_submit(uint64_t pk, uint64_t r1cs, const uint64_t* z, const uint64_t* r, const uint64_t* s) = 0;
   virtual void prove_collect_partial(uint64_t ticket, uint8_t* partial_out) = 0;
   virtual void prove_collect(uint64_t ticket, uint8_t* proof_out) = 0;

@@ -84,14 +84,25 @@ def submit_shared_wm(ctx, pk_h, r1cs_h, z: Optional[np.ndarray], group=None, dev
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     mask = wm_chain_mask(rank, world)
+    on_gpu = device is not None and str(device) != "cpu"
     with ctx.lock:
-        ticket, ptrs, nbytes = ctx.prove_begin_async(pk_h, r1cs_h, z, mask)
-        if mask != 7:
+        if mask == 7 or not on_gpu:
+            ticket, ptrs, nbytes = ctx.prove_begin_async(pk_h, r1cs_h, z, mask)
+            if mask != 7:
+                for k in range(3):
+                    dist.broadcast(chain_tensor(ptrs[k], nbytes, device), src=dist.get_global_rank(group, k % world) if group else k % world,
+                                   group=group)
+        else:
+            # stream-ordered exchange: torch's current stream waits for this rank's chains, the three NCCL broadcasts follow on
+            # it (ProcessGroupNCCL orders its own stream against the current one), and the finish step waits for that stream —
+            # the host enqueues and moves on, it never blocks between two proofs
+            stream = torch.cuda.current_stream(device).cuda_stream
+            ticket, ptrs, nbytes = ctx.prove_begin_async(pk_h, r1cs_h, z, mask | 0x80000000)
+            ctx.prove_chains_to_stream(ticket, stream)
             for k in range(3):
                 dist.broadcast(chain_tensor(ptrs[k], nbytes, device), src=dist.get_global_rank(group, k % world) if group else k % world,
                                group=group)
-            if device is not None and str(device) != "cpu":
-                torch.cuda.current_stream(device).synchronize()  # the chains must be in memory before the finish step reads them
+            ctx.prove_stream_to_finish(ticket, stream)
         ctx.prove_end_async(ticket)
     return ticket
 
