@@ -223,7 +223,17 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL_DEBUG is left as the launcher set it: fd 1 already points at stderr, so NCCL's banner / INFO lines (which the
         # driver reads to count the ranks) cannot mix with the one JSON line
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        # the chain broadcasts run while the accumulate kernels keep every SM full: give NCCL's kernels a high-priority stream
+        # (their CTAs are taken first when an SM drains) and few, small CTAs — the exchange is 3 x 32 MB per proof, latency matters
+        pg_opts = None
+        try:
+            pg_opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            if os.environ.get("ZKB_NCCL_MAX_CTAS"):
+                pg_opts.config.max_ctas = int(os.environ["ZKB_NCCL_MAX_CTAS"])
+        except Exception:                                     # older torch: default options
+            pg_opts = None
+        kw = {"pg_options": pg_opts} if pg_opts is not None else {}
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local), **kw)
 
     lib = Library()
     cid = CURVE_IDS[args.curve]

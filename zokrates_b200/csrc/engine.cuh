@@ -618,7 +618,7 @@ class Engine : public EngineBase {
     DevBuf<uint8_t> d_win;                    // result slots of the five MSMs
     HostBuf hw;                               // pinned landing zone of the same
     std::unique_ptr<StageTimer> tm, tm2;
-    Event ev_z_ready, ev_h_ready, ev_chains_done, ev_exchange, done;
+    Event ev_z_ready, ev_h_ready, ev_chains_done, ev_exchange, ev_plan_z, done;
     Stream fin; bool has_fin = false;         // waits for the five tails and copies the results out, off the main stream
     uint64_t pk = 0, r1cs = 0, ticket = 0;
     int state = 0;                            // 0 free, 1 begun (assignment MSMs enqueued), 2 fully enqueued (collectable)
@@ -627,7 +627,7 @@ class Engine : public EngineBase {
     std::future<FixedMults> fm;
     void destroy() {
       for (auto& w : ws) w.destroy();
-      ev_z_ready.destroy(); ev_h_ready.destroy(); ev_chains_done.destroy(); ev_exchange.destroy(); done.destroy();
+      ev_z_ready.destroy(); ev_h_ready.destroy(); ev_chains_done.destroy(); ev_exchange.destroy(); ev_plan_z.destroy(); done.destroy();
       if (has_fin) { stream_destroy(fin); has_fin = false; }
     }
   };
@@ -939,7 +939,7 @@ class Engine : public EngineBase {
     uint64_t total = n * pl.sh.W;
     if (total * nviews >= (1ull << 32)) throw Error(ZKB_E_ARG, "msm too large");
     // chunk size: aim for several waves of resident threads, at least 8 entries per chunk
-    uint64_t target = 600000;
+    uint64_t target = (uint64_t)opts.chunk_target;
     uint64_t T = (total + target - 1) / target;
     if (T < 8) T = 8;
     if (T > 64) T = 64;
@@ -1006,8 +1006,8 @@ class Engine : public EngineBase {
 
   MsmWs ws_misc_;       // standalone zkb_msm_g1 / g2
   // witness map + h-plan run on their own stream underneath the z-dependent MSMs
-  Stream wm_stream_;
-  bool has_wm_stream_ = false;
+  Stream wm_stream_, plan_stream_;
+  bool has_wm_stream_ = false, has_plan_stream_ = false;
   struct StreamScope {  // temporarily redirect every helper that launches on st_
     Stream& ref; Stream saved;
     StreamScope(Stream& r, Stream s) : ref(r), saved(r) { ref = s; }
@@ -1022,6 +1022,7 @@ class Engine : public EngineBase {
     for (auto& sl : slots_) { if (sl.fm.valid()) sl.fm.wait(); sl.destroy(); }
     ws_misc_.destroy();
     if (has_wm_stream_) stream_destroy(wm_stream_);
+    if (has_plan_stream_) stream_destroy(plan_stream_);
   }
 
   // scratch of the batch-affine rounds: shared by all MSMs (the accumulations run one after the other on the main stream)
@@ -1580,23 +1581,48 @@ class Engine : public EngineBase {
     // (high-priority) stream and fill the multiply-pipe bubbles of the z-dependent MSMs running on the main stream.
     if (!has_wm_stream_) { wm_stream_ = stream_create_high_priority(); has_wm_stream_ = true; }
     sl.tm2.reset(new StageTimer(wm_stream_));
-    {
-      sl.ev_z_ready.record(st_);
+    sl.ev_z_ready.record(st_);                       // the assignment is in place (uploaded on the main stream, or resident)
+    // The digit / sort plan of the z-dependent MSMs needs nothing but z: it runs on its own stream, so that with two proofs in
+    // flight it overlaps the PREVIOUS proof's accumulate kernels (memory- and atomic-bound work under multiply-bound work)
+    // instead of heading the main stream (round 2, first half: 2.2-2.7 ms of the 17.5 ms main-stream time per proof).
+    const uint32_t pre_c_z = z_window_mode(sl.sparse_z) ? 0 : pk.pre_cz;
+    if (opts.plan_stream) {
+      if (!has_plan_stream_) { plan_stream_ = stream_create_high_priority(); has_plan_stream_ = true; }
+      const size_t span = tm.begin_on(plan_stream_, "msm_plan_z");
+      StreamScope sc(st_, plan_stream_);
+      sl.ev_z_ready.wait(st_);
+      plan_build(sl.plan_z, sl.z_src + 1 + pk.lo, pk.hi - pk.lo, 3, pk.skip.p, pre_c_z);
+      tm.end_on(plan_stream_, span);
+      sl.ev_plan_z.record(st_);
+    }
+    if (chain_mask == 7) {   // replicated witness map: underneath the z-dependent MSMs
       StreamScope sc(st_, wm_stream_);
       sl.ev_z_ready.wait(st_);
       wm_chains(r, sl, chain_mask, *sl.tm2);
       sl.ev_chains_done.record(st_);
+    } else {
+      // shared witness map: the other ranks wait for this rank's chains, so they run FIRST and alone on the main stream
+      // (0.5 ms with the GPU to themselves; underneath the accumulate kernels they took twice as long and h arrived
+      // late: wait_h 1.1 ms at 8 GPUs).  The exchange and the finish step then hide under this rank's z-dependent MSMs.
+      wm_chains(r, sl, chain_mask, tm);
+      sl.ev_chains_done.record(st_);
     }
-    tm.begin("msm_plan_z");
-    plan_build(sl.plan_z, sl.z_src + 1 + pk.lo, pk.hi - pk.lo, 3, pk.skip.p, z_window_mode(sl.sparse_z) ? 0 : pk.pre_cz);
-    tm.end();
+    if (opts.plan_stream) {
+      tm.begin("wait_plan_z");
+      sl.ev_plan_z.wait(st_);
+      tm.end();
+    } else {
+      tm.begin("msm_plan_z");
+      plan_build(sl.plan_z, sl.z_src + 1 + pk.lo, pk.hi - pk.lo, 3, pk.skip.p, pre_c_z);
+      tm.end();
+    }
     msm_exec<Fq2>(sl.plan_z, pk.b2.p, w_b2, sl.ws[4], &tm, "accum1_g2_b2", 2, "tail_g2_b2");
     msm_exec<Fq>(sl.plan_z, pk.l.p, w_l, sl.ws[1], &tm, "accum1_g1_l", 0, "tail_g1_l");
     msm_exec<Fq>(sl.plan_z, pk.a.p, w_a, sl.ws[2], &tm, "accum1_g1_a", 1, "tail_g1_a");
     msm_exec<Fq>(sl.plan_z, pk.b1.p, w_b1, sl.ws[3], &tm, "accum1_g1_b1", 2, "tail_g1_b1");
     sl.pk = pkh; sl.r1cs = rh; sl.ticket = next_ticket_++; sl.state = 1; sl.has_rs = false;
     // chains left to other ranks: the caller exchanges buffers next, so this rank's chains must be complete in memory
-    if (chain_mask != 7 && !no_host_sync) stream_sync(wm_stream_);
+    if (chain_mask != 7 && !no_host_sync) sl.ev_chains_done.sync();   // the host exchanges the buffers next: wait for the chains only
     return sl.ticket;
   }
 

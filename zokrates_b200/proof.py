@@ -107,7 +107,7 @@ class VerificationKey:
 
     def to_tagged_json(self) -> str:
         """TaggedVerificationKey: scheme, curve, then the flattened vk (tagged.rs:7-13)."""
-        return json.dumps({"scheme": self.scheme, "curve": self.curve, "alpha": self.alpha.to_json(),
+        return json.dumps({"scheme": SCHEME_NAME, "curve": self.curve, "alpha": self.alpha.to_json(),
                            "beta": self.beta.to_json(), "gamma": self.gamma.to_json(), "delta": self.delta.to_json(),
                            "gamma_abc": [g.to_json() for g in self.gamma_abc]}, indent=2)
 
