@@ -92,8 +92,8 @@ int32_t zkb_pk_table_info(zkb_ctx* ctx, uint64_t pk_handle, uint64_t out[8]);
                                  * one serial inversion per block makes it 3.3x slower than the direct path on B200 as implemented
                                  * (profiles/r02_batch_affine.md); kept as a tested experimental path */
 #define ZKB_OPT_BATCH_AFFINE_MIN_LOG 11 /* smallest sorted list (log2 entries) that gets the affine rounds; default 16 */
-#define ZKB_OPT_PLAN_STREAM 12  /* 1 (default): the digit/sort plan of the assignment MSMs runs on its own stream and overlaps the previous
-                                 * proof's accumulate kernels; 0: it heads the main stream (round-1 order) */
+#define ZKB_OPT_PLAN_STREAM 12  /* 1: the digit/sort plan of the assignment MSMs runs on its own stream and overlaps the previous proof's
+                                 * accumulate kernels; 0 (default): it heads the main stream.  Measured equal on B200 (work-bound) */
 #define ZKB_OPT_CHUNK_TARGET 13 /* aimed-at number of accumulate chunks per MSM (default 600000); chunk length = entries / target in 8..64 */
 #define ZKB_OPT_NTT_KERNEL 9    /* tile pass of the NTT: 2 (default) four-step twiddles + cp.async tile load, 1 the round-1 pass */
 #define ZKB_OPT_PK_CACHE 8      /* 1 (default): zkb_pk_load of bytes that are already resident returns a handle onto the same key

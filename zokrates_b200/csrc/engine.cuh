@@ -1584,7 +1584,8 @@ class Engine : public EngineBase {
     sl.ev_z_ready.record(st_);                       // the assignment is in place (uploaded on the main stream, or resident)
     // The digit / sort plan of the z-dependent MSMs needs nothing but z: it runs on its own stream, so that with two proofs in
     // flight it overlaps the PREVIOUS proof's accumulate kernels (memory- and atomic-bound work under multiply-bound work)
-    // instead of heading the main stream (round 2, first half: 2.2-2.7 ms of the 17.5 ms main-stream time per proof).
+    // instead of heading the main stream.  Measured: no gain (17.47 vs 17.46 ms per proof) — the GPU is work-bound and the
+    // overlapped plan slows the accumulate kernels by what it saves; kept as an option, off by default.
     const uint32_t pre_c_z = z_window_mode(sl.sparse_z) ? 0 : pk.pre_cz;
     if (opts.plan_stream) {
       if (!has_plan_stream_) { plan_stream_ = stream_create_high_priority(); has_plan_stream_ = true; }
