@@ -233,6 +233,11 @@ int32_t zkb_prog_public_inputs(zkb_ctx* ctx, uint64_t prog_handle, uint64_t* out
  * proof_out = A.x | A.y | B.x.c0 | B.x.c1 | B.y.c0 | B.y.c1 | C.x | C.y like the Groth16 proof.  The R1CS -> SAP witness map, the
  * five MSMs and the transforms run on the device with the Groth16 kernels.  ark-gm17's sources are not part of the reference
  * tree: restated in oracle/gm17.py, parity unpinned against real ark-gm17 output. */
+/* zkb_gm17_setup: `impl NonUniversalBackend<T, GM17> for Ark`::setup (gm17.rs:19-41 -> ark-gm17 generate_parameters) from an explicit
+ * trapdoor (alpha, beta, gamma, tau, g1 generator scalar, g2 generator scalar; 6 x 32 bytes canonical LE) — fixed-base multiples on
+ * the device, key written in ark's serialize_unchecked layout.  The verifying key is the head of the proving key. */
+int32_t zkb_gm17_setup_size(zkb_ctx* ctx, uint64_t r1cs_handle, size_t* len);
+int32_t zkb_gm17_setup(zkb_ctx* ctx, uint64_t r1cs_handle, const uint64_t* trapdoor6, uint8_t* pk_out, size_t cap, size_t* len);
 int32_t zkb_gm17_pk_load(zkb_ctx* ctx, const uint8_t* pk_bytes, size_t len, uint64_t* pk_handle);
 int32_t zkb_gm17_pk_free(zkb_ctx* ctx, uint64_t pk_handle);
 int32_t zkb_gm17_prove(zkb_ctx* ctx, uint64_t pk_handle, uint64_t r1cs_handle, const uint64_t* z, const uint64_t d1[4],

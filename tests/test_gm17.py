@@ -28,6 +28,8 @@ def _check(lib, curve_name, ncons, npub, npriv, seed, verify=True):
     td = gm17.Gm17Trapdoor(3 + seed, 5, 7, 1234567 + seed, 11, 13)
     pk = gm17.setup(c, r1cs, td)
     pk_bytes = gm17.pk_serialize(c, pk)
+    # the device setup writes the same key bytes as the oracle's
+    assert backend.B200.setup_gm17(pprog, [td.alpha, td.beta, td.gamma, td.tau, td.g1_k, td.g2_k], lib=lib) == pk_bytes
     entropy = f"gm17-{seed}"
     orng = ark.rng_from_entropy(entropy)
     d1, d2, r = ark.fr_rand(c, orng), ark.fr_rand(c, orng), ark.fr_rand(c, orng)

@@ -30,7 +30,7 @@ SYMBOLS = [
     "zkb_groth16_prove_collect_partial", "zkb_groth16_prove_begin_async", "zkb_groth16_prove_end_async",
     "zkb_groth16_prove_chains_to_stream", "zkb_groth16_prove_stream_to_finish",
     "zkb_prog_load", "zkb_prog_info", "zkb_prog_free", "zkb_prog_compute_witness", "zkb_prog_set_witness",
-    "zkb_prog_public_inputs", "zkb_gm17_pk_load", "zkb_gm17_pk_free", "zkb_gm17_prove",
+    "zkb_prog_public_inputs", "zkb_gm17_pk_load", "zkb_gm17_pk_free", "zkb_gm17_prove", "zkb_gm17_setup", "zkb_gm17_setup_size",
 ]
 
 OPT_TABLES, OPT_TABLE_MIN_LOG, OPT_TABLE_C, OPT_Z_MODE, OPT_NTT_TILE_MIN, OPT_NTT_MAX_S, OPT_BITSUM_RADIX, OPT_PK_CACHE, OPT_NTT_KERNEL, OPT_BATCH_AFFINE, OPT_BATCH_AFFINE_MIN_LOG = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11
@@ -97,6 +97,8 @@ class Library:
         d.zkb_groth16_finalize_prepare.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         d.zkb_r1cs_check.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, _u64p]
         d.zkb_witness_eval.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, _u64p]
+        d.zkb_gm17_setup_size.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_size_t)]
+        d.zkb_gm17_setup.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         d.zkb_gm17_pk_load.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, _u64p]
         d.zkb_gm17_pk_free.argtypes = [C.c_void_p, C.c_uint64]
         d.zkb_gm17_prove.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
@@ -401,6 +403,16 @@ class Context:
         return fr_from_array(out[:n.value])
 
     # -- GM17
+    def gm17_setup(self, r1cs: int, trapdoor6) -> bytes:
+        td = fr_array([int(v) for v in trapdoor6])
+        assert td.shape == (6, 4)
+        n = C.c_size_t(0)
+        self.lib.check(self.lib.dll.zkb_gm17_setup_size(self.h, r1cs, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.uint8)
+        ln = C.c_size_t(0)
+        self.lib.check(self.lib.dll.zkb_gm17_setup(self.h, r1cs, td.ctypes.data, out.ctypes.data, len(out), C.byref(ln)))
+        return out[:ln.value].tobytes()
+
     def gm17_pk_load(self, pk_bytes: bytes) -> int:
         buf = np.frombuffer(pk_bytes, dtype=np.uint8)
         h = C.c_uint64(0)

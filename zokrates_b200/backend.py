@@ -143,6 +143,24 @@ class B200:
         return Proof.from_raw(c, raw, inputs)
 
     @staticmethod
+    def setup_gm17(program: Prog, trapdoor, device: int = 0, lib: Optional[_lib.Library] = None) -> bytes:
+        """`impl NonUniversalBackend<T, GM17> for Ark`::setup (zokrates_ark/src/gm17.rs:19-41) on the GPU.  `trapdoor`: an `StdRng`
+        (alpha, beta, gamma, tau and the two generator scalars are drawn with `fr_rand`, in that order) or 6 explicit integers.
+        Returns ark-gm17's `ProvingKey::serialize_unchecked` bytes (the verifying key is their head)."""
+        c = _curve(program.curve)
+        td = [fr_rand(c, trapdoor) for _ in range(6)] if isinstance(trapdoor, StdRng) else [int(v) % c.r for v in trapdoor]
+        if len(td) != 6 or any(v == 0 for v in td[:3] + td[4:]):
+            raise ValueError("trapdoor needs 6 scalars; alpha, beta, gamma and the generator scalars must be non-zero")
+        r1cs = synthesize(program)
+        ctx = context(c, device, lib)
+        with ctx.lock:
+            h = ctx.r1cs_load(r1cs.num_constraints, r1cs.num_instance, r1cs.num_witness, r1cs.matrices())
+            try:
+                return ctx.gm17_setup(h, td)
+            finally:
+                ctx.r1cs_free(h)
+
+    @staticmethod
     def generate_proof_gm17(program: Prog, witness: Witness, proving_key, rng: StdRng, device: int = 0,
                             lib: Optional[_lib.Library] = None) -> Proof:
         """`impl Backend<T, GM17> for Ark`::generate_proof (zokrates_ark/src/gm17.rs:43-75) on the GPU: the proving key is ark-gm17's

@@ -370,6 +370,15 @@ int32_t zkb_gm17_prove(zkb_ctx* ctx, uint64_t pk, uint64_t r1cs, const uint64_t*
     ctx->eng->gm17_prove(pk, r1cs, z, d1, d2, r, proof_out);
   });
 }
+int32_t zkb_gm17_setup_size(zkb_ctx* ctx, uint64_t r1cs, size_t* len) {
+  return guard(ctx, [&] { if (!len) throw Error(ZKB_E_ARG, "null"); *len = ctx->eng->gm17_setup_size(r1cs); });
+}
+int32_t zkb_gm17_setup(zkb_ctx* ctx, uint64_t r1cs, const uint64_t* trapdoor6, uint8_t* pk_out, size_t cap, size_t* len) {
+  return guard(ctx, [&] {
+    if (!trapdoor6 || !pk_out || !len) throw Error(ZKB_E_ARG, "null argument");
+    ctx->eng->gm17_setup(r1cs, trapdoor6, pk_out, cap, len);
+  });
+}
 int32_t zkb_field_op(zkb_ctx* ctx, int32_t field, int32_t op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n) {
   return guard(ctx, [&] {
     if (!a || !out) throw Error(ZKB_E_ARG, "null argument");

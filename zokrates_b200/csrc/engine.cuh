@@ -1979,6 +1979,8 @@ class Engine : public EngineBase {
   template <class F, class HX> HX gm17_msm(const Fr* scalars, const Affine<F>* pts, uint64_t n, bool replan);
   void gm17_prove(uint64_t pk, uint64_t r1cs, const uint64_t* z, const uint64_t* d1, const uint64_t* d2, const uint64_t* r,
                   uint8_t* proof_out) override;
+  size_t gm17_setup_size(uint64_t rh) override;
+  void gm17_setup(uint64_t rh, const uint64_t* trapdoor6, uint8_t* pk_out, size_t cap, size_t* len) override;
 
   // ------------------------------------------------------------------------------ setup (see setup.cuh)
   template <class F> void fb_build(FixedBase<F>& fb, Affine<F> stdgen, const uint32_t* gk);

@@ -72,6 +72,8 @@ struct EngineBase {
   virtual void gm17_pk_free(uint64_t h) = 0;
   virtual void gm17_prove(uint64_t pk, uint64_t r1cs, const uint64_t* z, const uint64_t* d1, const uint64_t* d2, const uint64_t* r,
                           uint8_t* proof_out) = 0;
+  virtual size_t gm17_setup_size(uint64_t r1cs) = 0;
+  virtual void gm17_setup(uint64_t r1cs, const uint64_t* trapdoor6, uint8_t* pk_out, size_t cap, size_t* len) = 0;
   virtual size_t setup_size(uint64_t r1cs) = 0;
   virtual void setup(uint64_t r1cs, const uint64_t* trapdoor7, uint8_t* pk_out, size_t cap, size_t* len) = 0;
   std::vector<std::pair<const char*, double>> timings;

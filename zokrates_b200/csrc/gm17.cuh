@@ -10,6 +10,7 @@
 // MSMs run one after the other without window tables (this path is about coverage, not the headline).
 #pragma once
 #include "engine.cuh"
+#include "setup.cuh"
 
 namespace zkb {
 
@@ -212,6 +213,185 @@ void Engine<C>::gm17_prove(uint64_t pkh, uint64_t rh, const uint64_t* z, const u
   const HG2A pb = HG2X::to_affine(gb);
   auto put = [&](size_t slot, const HFq& v) { HFq c = HFq::from_mont(v); memcpy(proof_out + slot * FQB, c.v, FQB); };
   put(0, pa.x); put(1, pa.y); put(2, pb.x.c0); put(3, pb.x.c1); put(4, pb.y.c0); put(5, pb.y.c1); put(6, pcc.x); put(7, pcc.y);
+}
+
+// ---- circuit-specific GM17 setup from an explicit trapdoor (alpha, beta, gamma, tau, g1_k, g2_k) ---------------------------------
+// `impl NonUniversalBackend<T, GM17> for Ark`::setup (zokrates_ark/src/gm17.rs:19-41) -> ark-gm17 `generate_parameters`; the trapdoor
+// is explicit as in zkb_groth16_setup (the reference draws it from its rng).  u = Lagrange coefficients at tau over the SAP domain;
+// per SAP variable  a_i = sum_rows (u_2r + u_2r+1) A_r[i] + (u_2r - u_2r+1) B_r[i] (+ the input-consistency rows),
+// c_i = sum_rows 4 u_2r C_r[i] (+ ...), extra variables x_r: c = u_2r + u_2r+1, y_j: c = u_(e+2j-1) + u_(e+2j); then every key element is a
+// fixed-base multiple of g or h (same window tables as the Groth16 setup).  Key bytes: ark's `serialize_unchecked` field order.
+template <class C>
+size_t Engine<C>::gm17_setup_size(uint64_t rh) {
+  R1cs& r = get_r1cs(rh);
+  const uint64_t rows = 2 * r.N + 2 * (r.ni - 1) + 1, nv = r.m + r.N + (r.ni - 1);
+  size_t n = 1;
+  while (n < rows) n <<= 1;
+  return 3 * G2B + 2 * G1B + (8 + r.ni * G1B) + (8 + nv * G1B) + (8 + nv * G2B) + (8 + (nv - r.ni) * G1B) + (8 + nv * G1B) + 3 * G1B + G2B +
+         (8 + (n + 1) * G1B);
+}
+
+template <class C>
+void Engine<C>::gm17_setup(uint64_t rh, const uint64_t* trapdoor6, uint8_t* pk_out, size_t cap, size_t* len) {
+  typedef typename GenOf<C>::T Gen;
+  R1cs& r = get_r1cs(rh);
+  const uint32_t N = (uint32_t)r.N, ni = (uint32_t)r.ni, m = (uint32_t)r.m;
+  const uint64_t rows = 2 * (uint64_t)N + 2 * (ni - 1) + 1;
+  const uint32_t nv = m + N + (ni - 1);
+  uint32_t lg = 0;
+  while (((uint64_t)1 << lg) < rows) lg++;
+  const size_t n = (size_t)1 << lg;
+  const size_t total = gm17_setup_size(rh);
+  if (cap < total) throw Error(ZKB_E_ARG, "pk_out too small");
+  DomainT& d = domain(lg);
+  Fr td[4];
+  for (int k = 0; k < 4; k++) {
+    Fr c;
+    for (int i = 0; i < 8; i++) c.v[i] = ((const uint32_t*)trapdoor6)[k * 8 + i];
+    td[k] = Fr::to_mont(c);
+  }
+  const Fr alpha = td[0], beta = td[1], gamma = td[2], tau = td[3];
+  Fr tn = tau;
+  for (uint32_t i = 0; i < lg; i++) tn = Fr::sqr(tn);
+  const Fr zt = Fr::sub(tn, Fr::one());
+  const Fr ab = Fr::add(alpha, beta), g2 = Fr::sqr(gamma), abg = Fr::mul(ab, gamma), gz = Fr::mul(gamma, zt);
+  const Fr g2z = Fr::mul(g2, zt), g2z2x2 = Fr::dbl(g2z);
+  // u = ifft(powers of tau) in natural order; powers up to tau^n scaled by gamma^2 Z for g_gamma2_z_t
+  DevBuf<Fr> pw(n), u(n), pwz(n + 1);
+  {
+    Fr one = Fr::one();
+    Fr* pp = pw.p; Fr* pz = pwz.p;
+    launch<k_ntt_table>(st_, n, ZKB_LAMBDA(size_t t) { ntt_powers_body<Fr>(tau, one, pp, (uint32_t)n, (uint32_t)t); });
+    launch<k_ntt_table>(st_, n + 1, ZKB_LAMBDA(size_t t) { ntt_powers_body<Fr>(tau, g2z, pz, (uint32_t)n + 1, (uint32_t)t); });
+    d2d(st_, u.p, pw.p, n * FRB);
+    ntt_dif(u.p, d.tw_inv.p, lg);
+    scratch_a_.ensure(n);
+    Fr* src = u.p; Fr* dst = scratch_a_.p;
+    Fr ninv = d.ninv;
+    launch<k_ntt_brev>(st_, n, ZKB_LAMBDA(size_t t) { dst[bitrev32((uint32_t)t, lg)] = Fr::mul(src[t], ninv); });
+    d2d(st_, u.p, scratch_a_.p, n * FRB);
+  }
+  // per R1CS row: u_2r + u_2r+1, u_2r - u_2r+1, 4 u_2r
+  DevBuf<Fr> urow[3];
+  for (int k = 0; k < 3; k++) urow[k].alloc(N ? N : 1);
+  {
+    const Fr* uu = u.p; Fr* p0 = urow[0].p; Fr* p1 = urow[1].p; Fr* p2 = urow[2].p;
+    launch<k_setup_scalars>(st_, N, ZKB_LAMBDA(size_t i) {
+      p0[i] = Fr::add(uu[2 * i], uu[2 * i + 1]);
+      p1[i] = Fr::sub(uu[2 * i], uu[2 * i + 1]);
+      p2[i] = Fr::dbl(Fr::dbl(uu[2 * i]));
+    });
+  }
+  // transposed products (CSC built on the host, as in the Groth16 setup)
+  DevBuf<Fr> abc[3];
+  for (int k = 0; k < 3; k++) {
+    const std::vector<uint32_t>& rp = r.h_rowptr[k];
+    const std::vector<uint32_t>& cl = r.h_col[k];
+    const size_t nnz = cl.size();
+    std::vector<uint32_t> colptr(m + 1, 0), rowidx(nnz), perm(nnz);
+    for (size_t i = 0; i < nnz; i++) colptr[cl[i] + 1]++;
+    for (uint32_t i = 0; i < m; i++) colptr[i + 1] += colptr[i];
+    std::vector<uint32_t> cur(colptr.begin(), colptr.end() - 1);
+    for (uint32_t row = 0; row < N; row++)
+      for (uint32_t e = rp[row]; e < rp[row + 1]; e++) {
+        uint32_t pos = cur[cl[e]]++;
+        rowidx[pos] = row;
+        perm[pos] = e;
+      }
+    DevBuf<uint32_t> d_colptr(m + 1), d_rowidx(nnz ? nnz : 1), d_perm(nnz ? nnz : 1);
+    h2d(st_, d_colptr.p, colptr.data(), (m + 1) * 4);
+    h2d(st_, d_rowidx.p, rowidx.data(), nnz * 4);
+    h2d(st_, d_perm.p, perm.data(), nnz * 4);
+    abc[k].alloc(m);
+    Fr* out = abc[k].p;
+    const uint32_t* cp = d_colptr.p; const uint32_t* ri = d_rowidx.p; const uint32_t* pm = d_perm.p;
+    const Fr* vl = r.val[k].p; const Fr* uu = urow[k].p;
+    launch<k_setup_scalars>(st_, m, ZKB_LAMBDA(size_t t) {
+      Fr acc = Fr::zero();
+      for (uint32_t e = cp[t]; e < cp[t + 1]; e++) acc = Fr::add(acc, Fr::mul(vl[pm[e]], uu[ri[e]]));
+      out[t] = acc;
+    });
+    stream_sync(st_);
+  }
+  // a_i and c_i of every SAP variable
+  DevBuf<Fr> va(nv), vc(nv);
+  {
+    const Fr* pA = abc[0].p; const Fr* pB = abc[1].p; const Fr* pC = abc[2].p; const Fr* uu = u.p; const Fr* uadd = urow[0].p;
+    Fr* pa = va.p; Fr* pc = vc.p;
+    const uint32_t e_off = 2 * N;
+    launch<k_setup_scalars>(st_, nv, ZKB_LAMBDA(size_t t) {
+      Fr a = Fr::zero(), c = Fr::zero();
+      if (t < m) {
+        a = Fr::add(pA[t], pB[t]);
+        c = pC[t];
+        if (t == 0) {
+          a = Fr::add(a, uu[e_off]);
+          c = Fr::add(c, uu[e_off]);
+          for (uint32_t j = 1; j < ni; j++) a = Fr::add(a, Fr::sub(uu[e_off + 2 * j - 1], uu[e_off + 2 * j]));
+        } else if (t < ni) {
+          a = Fr::add(a, Fr::add(uu[e_off + 2 * t - 1], uu[e_off + 2 * t]));
+          c = Fr::add(c, Fr::dbl(Fr::dbl(uu[e_off + 2 * t - 1])));
+        }
+      } else if (t < m + N) {
+        c = uadd[t - m];
+      } else {
+        const uint32_t j = (uint32_t)t - (m + N) + 1;
+        c = Fr::add(uu[e_off + 2 * j - 1], uu[e_off + 2 * j]);
+      }
+      pa[t] = a; pc[t] = c;
+    });
+  }
+  // scalar vectors of the queries
+  DevBuf<Fr> s_a(nv), s_q(ni), s_c1(nv - ni ? nv - ni : 1), s_c2(nv), ks(9);
+  {
+    const Fr* pa = va.p; const Fr* pc = vc.p;
+    Fr* oa = s_a.p; Fr* oq = s_q.p; Fr* o1 = s_c1.p; Fr* o2 = s_c2.p;
+    launch<k_setup_scalars>(st_, nv, ZKB_LAMBDA(size_t t) {
+      oa[t] = Fr::mul(gamma, pa[t]);
+      o2[t] = Fr::mul(g2z2x2, pa[t]);
+      const Fr mix = Fr::add(Fr::mul(g2, pc[t]), Fr::mul(abg, pa[t]));
+      if (t < ni) oq[t] = Fr::add(Fr::mul(gamma, pc[t]), Fr::mul(ab, pa[t]));
+      else o1[t - ni] = mix;
+    });
+    Fr hostk[9] = {Fr::one(), alpha, beta, gamma, gz, Fr::mul(abg, zt), Fr::mul(g2z, zt), Fr::zero(), Fr::zero()};
+    h2d(st_, ks.p, hostk, sizeof(hostk));
+  }
+  FixedBase<Fq> fb1;
+  FixedBase<Fq2> fb2;
+  DevBuf<uint32_t> gk(16);
+  h2d(st_, gk.p, trapdoor6 + 4 * 4, 64);
+  fb_build<Fq>(fb1, std_g1<Gen, Fq>(), gk.p);
+  fb_build<Fq2>(fb2, std_g2<Gen, Fq2>(), gk.p + 8);
+  DevBuf<uint8_t> out(total);
+  uint8_t* ob = out.p;
+  auto emit = [&](auto& fb, const Fr* scalars, size_t count, size_t byte_off) { fb_emit(fb, scalars, count, (uint32_t*)(ob + byte_off)); };
+  auto put_len = [&](uint64_t v, size_t byte_off) { h2d(st_, ob + byte_off, &v, 8); stream_sync(st_); };
+  size_t off = 0;
+  emit(fb2, ks.p + 0, 1, off); off += G2B;                     // vk.h_g2
+  emit(fb1, ks.p + 1, 1, off); off += G1B;                     // vk.g_alpha_g1
+  emit(fb2, ks.p + 2, 1, off); off += G2B;                     // vk.h_beta_g2
+  emit(fb1, ks.p + 3, 1, off); off += G1B;                     // vk.g_gamma_g1
+  emit(fb2, ks.p + 3, 1, off); off += G2B;                     // vk.h_gamma_g2
+  put_len(ni, off); off += 8;
+  emit(fb1, s_q.p, ni, off); off += (size_t)ni * G1B;          // vk.query
+  put_len(nv, off); off += 8;
+  emit(fb1, s_a.p, nv, off); off += (size_t)nv * G1B;          // a_query
+  put_len(nv, off); off += 8;
+  emit(fb2, s_a.p, nv, off); off += (size_t)nv * G2B;          // b_query
+  put_len(nv - ni, off); off += 8;
+  emit(fb1, s_c1.p, nv - ni, off); off += (size_t)(nv - ni) * G1B;   // c_query_1
+  put_len(nv, off); off += 8;
+  emit(fb1, s_c2.p, nv, off); off += (size_t)nv * G1B;         // c_query_2
+  emit(fb1, ks.p + 4, 1, off); off += G1B;                     // g_gamma_z
+  emit(fb2, ks.p + 4, 1, off); off += G2B;                     // h_gamma_z
+  emit(fb1, ks.p + 5, 1, off); off += G1B;                     // g_ab_gamma_z
+  emit(fb1, ks.p + 6, 1, off); off += G1B;                     // g_gamma2_z2
+  put_len(n + 1, off); off += 8;
+  emit(fb1, pwz.p, n + 1, off); off += (n + 1) * G1B;          // g_gamma2_z_t
+  if (off != total) throw Error(ZKB_E_INTERNAL, "gm17 setup size mismatch");
+  d2h(st_, pk_out, ob, total);
+  stream_sync(st_);
+  *len = total;
 }
 
 }  // namespace zkb
