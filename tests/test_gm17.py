@@ -42,6 +42,15 @@ def _check(lib, curve_name, ncons, npub, npriv, seed, verify=True):
     assert '"scheme": "gm17"' in proof.to_tagged_json()
     if verify:
         assert gm17.verify(c, pk, pub, exp)
+        # the product's host verifier (B200.verify for GM17) agrees with the oracle's: accepts the proof, rejects a wrong input
+        from zokrates_b200.proof import Proof, gm17_vk_from_pk_bytes
+        from zokrates_b200.verify import verify_proof_gm17
+        from zokrates_b200.curves import curve as pcurve
+        vk = gm17_vk_from_pk_bytes(pcurve(curve_name), pk_bytes)
+        assert verify_proof_gm17(vk, proof)
+        bad = Proof.from_raw(pcurve(curve_name), proof.to_raw(), [(pub[0] + 1) % c.r] + pub[1:], scheme="gm17")
+        assert not verify_proof_gm17(vk, bad)
+        assert '"scheme": "gm17"' in vk.to_tagged_json()
     return c, pk, r1cs, z, td
 
 

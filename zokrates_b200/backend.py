@@ -224,6 +224,12 @@ class B200:
         return SetupKeypair(vk_from_pk_bytes(c, pk), pk)
 
     @staticmethod
+    def verify_gm17(vk, proof: Proof) -> bool:
+        """`impl Backend<T, GM17> for Ark`::verify (gm17.rs:77-117): both GM17 pairing equations, on the host."""
+        from .verify import verify_proof_gm17
+        return verify_proof_gm17(vk, proof)
+
+    @staticmethod
     def verify(vk, proof: Proof) -> bool:
         """Pairing check on the host (verification is not a GPU path)."""
         from .verify import verify_proof

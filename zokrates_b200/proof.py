@@ -151,3 +151,43 @@ def vk_from_pk_bytes(c: Curve, pk: bytes) -> VerificationKey:
     cnt = int.from_bytes(pk[off:off + 8], "little"); off += 8
     abc = [g1() for _ in range(cnt)]
     return VerificationKey(alpha, beta, gamma, delta, abc, c.name)
+
+
+@dataclass
+class Gm17VerificationKey:
+    """`VerificationKey<G1, G2>` of scheme/gm17.rs:19-26: h, g_alpha, h_beta, g_gamma, h_gamma, query."""
+    h: G2Affine
+    g_alpha: G1Affine
+    h_beta: G2Affine
+    g_gamma: G1Affine
+    h_gamma: G2Affine
+    query: List[G1Affine]
+    curve: str = "bn128"
+
+    def to_tagged_json(self) -> str:
+        return json.dumps({"scheme": "gm17", "curve": self.curve, "h": self.h.to_json(), "g_alpha": self.g_alpha.to_json(),
+                           "h_beta": self.h_beta.to_json(), "g_gamma": self.g_gamma.to_json(), "h_gamma": self.h_gamma.to_json(),
+                           "query": [g.to_json() for g in self.query]}, indent=2)
+
+
+def gm17_vk_from_pk_bytes(c: Curve, pk: bytes) -> Gm17VerificationKey:
+    """The `vk` prefix of ark-gm17's ProvingKey layout re-encoded as the reference's hex VK (zokrates_ark/src/gm17.rs:29-36)."""
+    n = c.fq_bytes
+    off = 0
+
+    def g1():
+        nonlocal off
+        raw = bytearray(pk[off:off + 2 * n]); off += 2 * n
+        raw[-1] &= 0x3F
+        return G1Affine(_hex(bytes(raw[:n])), _hex(bytes(raw[n:])))
+
+    def g2():
+        nonlocal off
+        raw = bytearray(pk[off:off + 4 * n]); off += 4 * n
+        raw[-1] &= 0x3F
+        f = [_hex(bytes(raw[i * n:(i + 1) * n])) for i in range(4)]
+        return G2Affine((f[0], f[1]), (f[2], f[3]))
+
+    h, g_alpha, h_beta, g_gamma, h_gamma = g2(), g1(), g2(), g1(), g2()
+    cnt = int.from_bytes(pk[off:off + 8], "little"); off += 8
+    return Gm17VerificationKey(h, g_alpha, h_beta, g_gamma, h_gamma, [g1() for _ in range(cnt)], c.name)

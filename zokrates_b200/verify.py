@@ -294,3 +294,40 @@ def verify_proof(vk: VerificationKey, proof: Proof) -> bool:
         return pr.product_is_one([(negA, B), (alpha, beta), (acc, gamma), (C, delta)])
     except DegeneratePoint:
         return False                                  # the reference's verify returns false here, it does not crash
+
+
+def verify_proof_gm17(vk, proof: Proof) -> bool:
+    """`impl Backend<T, GM17> for Ark`::verify (zokrates_ark/src/gm17.rs:77-117 -> ark-gm17 `verify_proof`), on the host:
+        e(A + G^alpha, B + H^beta) = e(G^alpha, H^beta) e(psi, H^gamma) e(C, H),   e(A, H^gamma) = e(G^gamma, B),
+    psi = query_0 + sum x_i query_i.  Malformed input raises, as the reference panics."""
+    if vk.curve != proof.curve:
+        raise ValueError("proof and verification key are for different curves")
+    pr = _pairing(vk.curve)
+    c = pr.c
+    inputs = proof.input_values()
+    if len(inputs) + 1 != len(vk.query):
+        raise ValueError("MalformedVerifyingKey: %d public inputs for %d query points" % (len(inputs), len(vk.query)))
+    if any(x >= c.r for x in inputs):
+        raise ValueError("public input not reduced")
+    A, C = _g1(proof.proof.a, c.p), _g1(proof.proof.c, c.p)
+    B = _g2(proof.proof.b, c.p)
+    g_alpha, g_gamma = _g1(vk.g_alpha, c.p), _g1(vk.g_gamma, c.p)
+    h, h_beta, h_gamma = _g2(vk.h, c.p), _g2(vk.h_beta, c.p), _g2(vk.h_gamma, c.p)
+    query = [_g1(g, c.p) for g in vk.query]
+    for pt in [A, C, g_alpha, g_gamma] + query:
+        if not pr.on_g1(pt):
+            raise ValueError("G1 point is not on the curve")
+    for q in (B, h, h_beta, h_gamma):
+        if q is not None and not pr.on_curve12(pr.twist(q)):
+            raise ValueError("G2 point is not on the curve")
+    psi = query[0]
+    for x, g in zip(inputs, query[1:]):
+        psi = pr.g1_add(psi, pr.g1_mul(g, x))
+    neg = lambda P: None if P is None else (P[0], (-P[1]) % c.p)     # noqa: E731
+    # e(A, B + H^beta) e(G^alpha, B) = e(psi, H^gamma) e(C, H)   (the e(G^alpha, H^beta) terms cancel: no G2 addition needed)
+    try:
+        first = pr.product_is_one([(A, B), (A, h_beta), (g_alpha, B), (neg(psi), h_gamma), (neg(C), h)])
+        second = pr.product_is_one([(A, h_gamma), (neg(g_gamma), B)])
+    except DegeneratePoint:
+        return False
+    return first and second
