@@ -233,3 +233,28 @@ def test_native_witness_matches_interpreter_gpu(case, gpu_lib):
     check_program(gpu_lib, prog, inputs)
     prog, inputs = random_program(prog.curve, 100 + case, n=200)
     check_program(gpu_lib, prog, inputs, try_oor=bool(case & 1))
+
+
+def test_program_cache_by_content_emu(emu_lib):
+    """The static trait method hands the program over on every call: a second zkb_prog_load of the same bytes is a handle onto the
+    resident program (also after the last handle was released), other bytes are not."""
+    ctx = Context(0, 0, emu_lib)
+    prog, inputs = solver_program("bn128", 8), [201, 77, 5]
+    data = zir.write_prog(prog)
+    h1 = ctx.prog_load(data)
+    assert "prog_cache_hit" not in ctx.timings()
+    h2 = ctx.prog_load(data)
+    assert h2 != h1 and "prog_cache_hit" in ctx.timings()
+    assert ctx.prog_info(h1)["r1cs"] == ctx.prog_info(h2)["r1cs"]
+    ref = ir.Interpreter().execute(prog, inputs).write()
+    assert ctx.prog_compute_witness(h2, inputs) == ref
+    ctx.prog_free(h1); ctx.prog_free(h2)
+    with pytest.raises(ZkbError):
+        ctx.prog_info(h2)
+    h3 = ctx.prog_load(data)                                                 # revived from the idle slot
+    assert "prog_cache_hit" in ctx.timings()
+    assert ctx.prog_compute_witness(h3, inputs) == ref
+    other = zir.write_prog(solver_program("bn128", 9))
+    h4 = ctx.prog_load(other)
+    assert "prog_cache_hit" not in ctx.timings()
+    ctx.prog_free(h3); ctx.prog_free(h4)
