@@ -255,7 +255,7 @@ def main():
     pk_h = ctx.pk_load(pk, rank, world)
     pk_bytes = len(pk)
     table_info = ctx.pk_table_info(pk_h)
-    keep_pk = rank == 0 and not args.skip_cpu_baseline and args.log_n <= CPU_SAMPLE_MAX_LOG_N
+    keep_pk = rank == 0 and args.log_n <= CPU_SAMPLE_MAX_LOG_N and (world == 1 or not args.skip_cpu_baseline)
     if not keep_pk:
         del pk
     z_pinned = torch.from_numpy(z).pin_memory()
@@ -367,6 +367,27 @@ def main():
     args.pipeline = saved_depth
     latency_ms = 1e3 * sorted(lat)[len(lat) // 2]
 
+    # the trait-shaped call: `Backend::generate_proof` is static and receives the key BYTES every time
+    # (zokrates_ark/src/groth16.rs:40-44), so one call = load the key by content (fingerprint of the bytes, the resident key and
+    # its window tables are found again: ZKB_OPT_PK_CACHE) + prove with z in host memory + release the handle.  One proof at a
+    # time, nothing in flight.  The R1CS stays loaded (a program cache of the same kind exists behind zkb_prog_load).
+    trait_call = None
+    if world == 1 and keep_pk:
+        tc = []
+        for _ in range(5):
+            barrier()
+            t0 = time.perf_counter()
+            h2 = ctx.pk_load(pk, 0, 1)
+            hit = "pk_cache_hit" in ctx.timings()
+            t1 = time.perf_counter()
+            ctx.prove(h2, r1cs_h, z_host, *r_s)
+            ctx.pk_free(h2)
+            tc.append((time.perf_counter() - t0, t1 - t0, hit))
+        tc.sort()
+        trait_call = {"ms_per_proof": 1e3 * tc[len(tc) // 2][0], "pk_load_by_content_ms": 1e3 * tc[len(tc) // 2][1], "cache_hit": bool(tc[len(tc) // 2][2]),
+                      "key_bytes": pk_bytes,
+                      "note": "zkb_pk_load(key bytes) -> fingerprint, cache hit + zkb_groth16_prove(z in host memory) + zkb_pk_free, sequential"}
+
     value = n_cons * args.steps / t_res
     e2e_value = n_cons * args.steps / t_e2e
 
@@ -471,6 +492,7 @@ def main():
             "gpu_launches": int(launches),
             "pipeline_depth": args.pipeline,
             "latency_ms_one_proof_e2e": latency_ms,
+            "trait_shaped_call": trait_call,
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

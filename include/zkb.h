@@ -95,6 +95,9 @@ int32_t zkb_pk_table_info(zkb_ctx* ctx, uint64_t pk_handle, uint64_t out[8]);
 #define ZKB_OPT_PLAN_STREAM 12  /* 1: the digit/sort plan of the assignment MSMs runs on its own stream and overlaps the previous proof's
                                  * accumulate kernels; 0 (default): it heads the main stream.  Measured equal on B200 (work-bound) */
 #define ZKB_OPT_CHUNK_TARGET 13 /* aimed-at number of accumulate chunks per MSM (default 600000); chunk length = entries / target in 8..64 */
+#define ZKB_OPT_CHAIN_SHARE 14  /* multi-GPU, world >= 3: the ranks that compute a witness-map chain (0, 1, 2) get a smaller slice of every
+                                 * query vector at zkb_pk_load; -1 (default) from a cost model, 0 equal shares, > 0 the chain's cost in
+                                 * 1/1000 of the whole MSM work.  Must be equal on all ranks (the cuts are derived independently). */
 #define ZKB_OPT_NTT_KERNEL 9    /* tile pass of the NTT: 2 (default) four-step twiddles + cp.async tile load, 1 the round-1 pass */
 #define ZKB_OPT_PK_CACHE 8      /* 1 (default): zkb_pk_load of bytes that are already resident returns a handle onto the same key
                                  * (content fingerprint), and the last key released by zkb_pk_free stays resident until another

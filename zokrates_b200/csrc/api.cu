@@ -160,6 +160,7 @@ int32_t zkb_ctx_set_option(zkb_ctx* ctx, int32_t opt, int64_t value) {
       case ZKB_OPT_BATCH_AFFINE_MIN_LOG: if (value < 0 || value > 40) throw Error(ZKB_E_ARG, "ZKB_OPT_BATCH_AFFINE_MIN_LOG"); o.batch_affine_min_log = value; break;
       case ZKB_OPT_PLAN_STREAM: if (value < 0 || value > 1) throw Error(ZKB_E_ARG, "ZKB_OPT_PLAN_STREAM: 0 or 1"); o.plan_stream = value; break;
       case ZKB_OPT_CHUNK_TARGET: if (value < 1000 || value > 100000000) throw Error(ZKB_E_ARG, "ZKB_OPT_CHUNK_TARGET: 1e3 .. 1e8"); o.chunk_target = value; break;
+      case ZKB_OPT_CHAIN_SHARE: if (value < -1 || value > 500) throw Error(ZKB_E_ARG, "ZKB_OPT_CHAIN_SHARE: -1, 0 or 1..500"); o.chain_share = value; break;
       case ZKB_OPT_NTT_KERNEL: if (value != 1 && value != 2) throw Error(ZKB_E_ARG, "ZKB_OPT_NTT_KERNEL: 1 or 2"); o.ntt_kernel = value; break;
       case ZKB_OPT_PK_CACHE: if (value < 0 || value > 1) throw Error(ZKB_E_ARG, "ZKB_OPT_PK_CACHE: 0 or 1"); o.pk_cache = value; break;
       case ZKB_OPT_BITSUM_RADIX: if (value != 2 && value != 8) throw Error(ZKB_E_ARG, "ZKB_OPT_BITSUM_RADIX: 2 or 8"); o.bitsum_radix = value; break;

@@ -12,6 +12,7 @@
 #include <memory>
 #include <vector>
 #include <chrono>
+#include <cmath>
 #include <future>
 #include "fp64.cuh"
 #include "msm.cuh"
@@ -1475,15 +1476,34 @@ class Engine : public EngineBase {
         w[i] = wi;
         total += wi;
       }
-      auto cut = [&](uint32_t k) -> uint64_t {   // first index whose prefix weight reaches total * k / world
+      // With three or more ranks the witness-map chains are computed once each by ranks 0, 1, 2 at the head of their main
+      // stream: those ranks get a smaller share of the MSM work so that all ranks reach the h-MSM together.
+      // f = one chain's cost as a fraction of the whole MSM work, from a model calibrated at 2^20 on B200 (a chain = 0.19 n
+      // log2(n)/20 weight units in BN254, 0.086 in BLS12-381, a weight unit = one G1 point through all windows);
+      // ZKB_OPT_CHAIN_SHARE: -1 model (default), 0 equal shares, > 0 f in 1/1000.
+      std::vector<double> cum(world + 1, 0.0);
+      {
+        double f = 0;
+        if (world >= 3 && opts.chain_share != 0) {
+          const double n_dom = (double)hl + 1, lg = std::log2(n_dom > 2 ? n_dom : 2);
+          const double chain_units = (Fq::N > 8 ? 0.086 : 0.19) * n_dom * lg / 20.0;
+          f = opts.chain_share > 0 ? opts.chain_share / 1000.0 : chain_units / (total + (double)hl);
+          const double fmax = 0.6 / world;                // an owner keeps at least ~40 % of an equal share
+          if (f > fmax) f = fmax;
+        }
+        for (uint32_t k = 0; k < world; k++) cum[k + 1] = cum[k] + (1.0 + 3.0 * f) / world - (k < 3 ? f : 0.0);
+        cum[world] = 1.0;
+      }
+      auto cut = [&](uint32_t k) -> uint64_t {   // first index whose prefix weight reaches this rank's cumulative share
         if (k == 0) return 0;
         if (k >= world) return na;
-        const double target = total * k / world;
+        const double target = total * cum[k];
         double acc = 0;
         for (uint64_t i = 0; i < na; i++) { if (acc >= target) return i; acc += w[i]; }
         return na;
       };
       p->lo = cut(rank); p->hi = cut(rank + 1);
+      p->hlo = (uint64_t)((double)hl * cum[rank]); p->hhi = rank + 1 == world ? hl : (uint64_t)((double)hl * cum[rank + 1]);
     }
     const uint64_t cnt = p->hi - p->lo, hcnt = p->hhi - p->hlo;
     p->a.alloc(cnt); p->b1.alloc(cnt); p->l.alloc(cnt); p->b2.alloc(cnt); p->h.alloc(hcnt);

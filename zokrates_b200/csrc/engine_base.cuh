@@ -18,6 +18,7 @@ struct Options {
   int64_t batch_affine = 0;   // ZKB_OPT_BATCH_AFFINE: rounds of pairwise affine additions (shared inversion) before the XYZZ accumulation; 0 = off
                               // (default: measured 3.3x SLOWER than the direct path on B200, profiles/r02_batch_affine.md)
   int64_t batch_affine_min_log = 16;   // ZKB_OPT_BATCH_AFFINE_MIN_LOG: only for lists of 2^k (pair, window) entries and more
+  int64_t chain_share = -1;   // ZKB_OPT_CHAIN_SHARE: MSM share taken off the ranks that compute a witness-map chain (world >= 3): -1 model, 0 none, > 0 per mille
   int64_t plan_stream = 0;    // ZKB_OPT_PLAN_STREAM: 1 = the z digit/sort plan runs on its own stream (overlaps the previous proof), 0 = heads the main
                               // stream (default: measured equal, 17.47 vs 17.46 ms — the GPU is work-bound, the overlap only slows the accumulate kernels)
   int64_t chunk_target = 600000;   // ZKB_OPT_CHUNK_TARGET: aimed-at number of accumulate chunks (threads) per MSM; chunk = entries / target, 8..64
