@@ -216,6 +216,9 @@ def test_native_errors_emu(emu_lib):
     with pytest.raises(ZkbError, match="no value yet"):
         ctx.prog_compute_witness(h, [3])
     ctx.prog_free(h)
+    # a directive must match its solver's signature (Solver::get_signature): Xor takes two inputs
+    with pytest.raises(ZkbError, match="signature"):
+        ctx.prog_load(zir.write_prog(Prog([Parameter.private_(x)], 0, [Directive([q(x)], [y], "Xor")], "bn128")))
     # a Zir solver has no device path
     zprog = Prog([Parameter.private_(x)], 0, [Directive([q(x)], [y], "Zir", None)], "bn128")
     h = ctx.prog_load(zir.write_prog(zprog).replace(b"cZir", b"cZir"))

@@ -34,6 +34,7 @@ static constexpr uint32_t PROG_DIRECTIVE = 0x80000000u;   // statement list: con
 struct Cbor {
   const uint8_t* d;
   size_t p, end;
+  Cbor(const uint8_t* data, size_t pos, size_t e) : d(data), p(pos), end(e) {}
   [[noreturn]] static void bad(const char* what) { throw Error(ZKB_E_FORMAT, std::string("program file: ") + what); }
   uint8_t byte() { if (p >= end) bad("CBOR item runs past the end of its section"); return d[p++]; }
   const uint8_t* take(size_t n) { if (n > end - p) bad("CBOR item runs past the end of its section"); const uint8_t* q = d + p; p += n; return q; }
@@ -53,7 +54,9 @@ struct Cbor {
   }
   bool at_break() { return p < end && d[p] == 0xff; }
   void skip_tags() { while (p < end && (d[p] >> 5) == 6) { uint32_t m; uint64_t a; bool i; head(m, a, i); } }
-  void skip() {   // one complete item
+  uint32_t depth = 0;
+  void skip() {   // one complete item (nesting bounded: a hostile file must not overflow the stack)
+    struct Guard { uint32_t& d; explicit Guard(uint32_t& x) : d(x) { if (++d > 128) bad("CBOR nesting too deep"); } ~Guard() { --d; } } g(depth);
     uint32_t major; uint64_t arg; bool indef;
     head(major, arg, indef);
     switch (major) {
@@ -331,7 +334,7 @@ inline void prog_parse(const uint8_t* data, size_t len, int curve, const uint32_
   // ark symbol table: instance / witness numbering in allocation order (zokrates_ark/src/lib.rs:47-73,94-113)
   static constexpr uint32_t WIT = 0x80000000u;   // symbol = index | WIT for witness variables
   std::unordered_map<int64_t, uint32_t> sym;
-  sym.reserve((size_t)n_cons + 64);
+  sym.reserve(std::min<size_t>((size_t)n_cons, len / 40) + 64);   // a constraint needs at least ~40 bytes: bound the header's claim by the file
   std::vector<int64_t> inst, wit;
   sym[0] = 0;
   inst.push_back(0);
@@ -342,7 +345,7 @@ inline void prog_parse(const uint8_t* data, size_t len, int curve, const uint32_
     else { sym[id] = (uint32_t)inst.size(); inst.push_back(id); }
   }
   std::vector<uint32_t> rsym[3];          // per matrix: symbol of every term (columns are fixed once ni is known)
-  for (int k = 0; k < 3; k++) { P.rowptr[k].reserve((size_t)n_cons + 1); P.rowptr[k].push_back(0); }
+  for (int k = 0; k < 3; k++) { P.rowptr[k].reserve(std::min<size_t>((size_t)n_cons, len / 40) + 1); P.rowptr[k].push_back(0); }
   auto add_comb = [&](int k, const std::vector<ProgTerm>& terms) {
     for (const ProgTerm& t : terms) {
       auto it = sym.find(t.var);
@@ -423,6 +426,20 @@ inline void prog_parse(const uint8_t* data, size_t len, int curve, const uint32_
           if ((uint64_t)sv.ref >= table.size()) Cbor::bad("solver index out of range");
           sv = table[(size_t)sv.ref];
           if (sv.ref >= 0) Cbor::bad("nested solver reference");
+        }
+        {  // Solver::get_signature (common/solvers.rs:47-63): the statement must carry exactly that many inputs and outputs
+          const uint32_t n_in = (uint32_t)(P.lc_ptr.size() - 1) / 2 - P.d_in_ptr.back();
+          const uint32_t n_out = (uint32_t)d_out_var.size() - P.d_out_ptr.back();
+          uint32_t want_in = n_in, want_out = n_out;
+          switch (sv.kind) {
+            case SOLVER_CONDITION_EQ: want_in = 1; want_out = 2; break;
+            case SOLVER_BITS: want_in = 1; want_out = sv.arg; break;
+            case SOLVER_DIV: case SOLVER_XOR: case SOLVER_OR: want_in = 2; want_out = 1; break;
+            case SOLVER_SHA_AXXA: case SOLVER_SHA_CH: want_in = 3; want_out = 1; break;
+            case SOLVER_EUCLIDEAN_DIV: want_in = 2; want_out = 2; break;
+            default: break;
+          }
+          if (n_in != want_in || n_out != want_out) Cbor::bad("directive does not match the signature of its solver");
         }
         P.d_kind.push_back(sv.kind); P.d_arg.push_back(sv.arg);
         P.d_in_ptr.push_back((uint32_t)(P.lc_ptr.size() - 1) / 2);
