@@ -183,3 +183,117 @@ def make(curve, inputs=(0, 0, 0, 5)):
 
     r1cs = R1CS(cv.name, len(bd.a), bd.n_inst, len(bd.z) - bd.n_inst, csr(bd.a), csr(bd.b), csr(bd.c))
     return r1cs, fr_array(bd.z), outs
+
+
+# ---- the same function as a PROGRAM with solver directives (what `zokrates compile` hands to compute-witness) ----------------
+class _ProgBuilder(_Builder):
+    """Emits IR statements instead of R1CS rows with values: every gadget is the directive that computes its output followed by
+    the constraints that pin it — `Bits` for the unpacking and the modular additions, `Xor`, `ShaCh`, `ShaAndXorAndXorAnd` for the
+    bit gadgets (zokrates_interpreter/src/lib.rs:249-307) — so witness generation has to run the solvers, as for a compiled program."""
+
+    def __init__(self, r, n_out, n_in):
+        super().__init__(r)
+        from .ir import Variable
+        self.V = Variable
+        self.st = []
+        self.n_out, self.n_in = n_out, n_in
+
+    def var(self, i):
+        if i == 0:
+            return self.V.one()
+        if i <= self.n_out:
+            return self.V.public(i - 1)
+        return self.V.new(i - 1 - self.n_out)           # arguments first: _0 .. _(n_in - 1)
+
+    def lc(self, terms):
+        from .ir import LinComb
+        return LinComb([(self.var(i), k % self.r) for i, k in terms])
+
+    def new(self, val=0):
+        self.z.append(0)
+        return len(self.z) - 1
+
+    def val(self, op):
+        return op[1] if isinstance(op, tuple) else 0
+
+    def row(self, a, b, c):
+        from .ir import Constraint, QuadComb
+        self.st.append(Constraint(QuadComb(self.lc(a), self.lc(b)), self.lc(c)))
+
+    def directive(self, solver, inputs, outputs, arg=None):
+        from .ir import Directive, QuadComb, LinComb
+        self.st.append(Directive([QuadComb(self.lc(t), LinComb.one()) for t in inputs], [self.var(o) for o in outputs], solver, arg))
+
+    def xor(self, x, y):
+        if isinstance(x, tuple) and isinstance(y, tuple):
+            return ("c", x[1] ^ y[1])
+        if isinstance(x, tuple):
+            x, y = y, x
+        if isinstance(y, tuple):
+            if y[1] == 0:
+                return x
+            out = self.new()
+            self.row([(0, 1), (x, self.r - 1)], [(0, 1)], [(out, 1)])            # not x: a definition
+            return out
+        out = self.new()
+        self.directive("Xor", [[(x, 1)], [(y, 1)]], [out])
+        self.row([(x, 2)], [(y, 1)], [(x, 1), (y, 1), (out, self.r - 1)])
+        return out
+
+    def ch(self, e, f, g):
+        out = self.new()
+        self.directive("ShaCh", [self.lin(e), self.lin(f), self.lin(g)], [out])
+        self.row(self.lin(e), self.lin(f) + self.lin(g, -1), [(out, 1)] + self.lin(g, -1))
+        return out
+
+    def maj(self, x, y, w):
+        t = self.new()
+        self.row(self.lin(x), self.lin(y), [(t, 1)])                               # t = x y: a definition
+        out = self.new()
+        self.directive("ShaAndXorAndXorAnd", [self.lin(w), self.lin(x), self.lin(y)], [out])   # x y - (2 x y - x - y) w
+        self.row(self.lin(x) + self.lin(y) + [(t, self.r - 2)], self.lin(w), [(out, 1), (t, self.r - 1)])
+        return out
+
+    def add_words(self, words, const=0):
+        nbits = max(33, (len(words) * ((1 << 32) - 1) + const).bit_length())
+        res = [self.new() for _ in range(nbits)]
+        lhs = [(0, const % self.r)] if const else []
+        for w in words:
+            for i, bit in enumerate(w):
+                lhs += self.lin(bit, 1 << i)
+        self.directive("Bits", [lhs], res[::-1], nbits)                            # big-endian outputs
+        for v in res:
+            self.boolean(v)
+        self.row(lhs, [(0, 1)], [(v, (1 << i) % self.r) for i, v in enumerate(res)])
+        return res[:32]
+
+
+def make_prog(curve):
+    """`def main(private field a, b, c, d) -> field[2]` = sha256packed as an IR program with solver directives."""
+    from .ir import Parameter, Prog
+    cv = _curve(curve)
+    bd = _ProgBuilder(cv.r, 2, 4)
+    out_vars = [bd.new(), bd.new()]
+    in_vars = [bd.new() for _ in range(4)]
+    msg_bits = []
+    for var in in_vars:
+        bits = [bd.new() for _ in range(128)]                                      # LSB first
+        bd.directive("Bits", [[(var, 1)]], bits[::-1], 128)
+        for bv in bits:
+            bd.boolean(bv)
+        bd.row([(var, 1)], [(0, 1)], [(bv, (1 << i) % cv.r) for i, bv in enumerate(bits)])
+        msg_bits += bits[::-1]
+    words = [msg_bits[32 * k:32 * k + 32][::-1] for k in range(16)]
+    state = [[("c", (iv >> i) & 1) for i in range(32)] for iv in IV]
+    state = _compress(bd, state, words)
+    pad = [0x80000000] + [0] * 14 + [512]
+    state = _compress(bd, state, [[("c", (p >> i) & 1) for i in range(32)] for p in pad])
+    dbits = []
+    for wd in state:
+        dbits += wd[::-1]
+    for k in range(2):
+        lhs = []
+        for i, bit in enumerate(dbits[128 * k:128 * k + 128]):
+            lhs += bd.lin(bit, 1 << (127 - i))
+        bd.row(lhs, [(0, 1)], [(out_vars[k], 1)])
+    return Prog([Parameter.private_(bd.var(v)) for v in in_vars], 2, bd.st, cv.name)
