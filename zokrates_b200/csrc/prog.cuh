@@ -172,6 +172,7 @@ struct ProgData {
   std::vector<uint8_t> defined;                       // per column: some statement (or an input) gives it a value
   std::string schedule_error;                         // non-empty: the statements cannot be scheduled (compute-witness refuses)
   uint64_t r1cs = 0;                                  // handle of the loaded matrices
+  mutable std::unordered_map<int64_t, uint32_t> col_of_var;   // IR variable id -> R1CS column, built on the first witness_parse
 };
 
 namespace prog_detail {
@@ -574,9 +575,11 @@ inline void witness_parse(const ProgData& P, const uint8_t* data, size_t len, co
   if (len < 8) bad("truncated");
   const uint64_t n = le64(data);
   if (n > (len - 8) / 40) bad("truncated");
-  std::unordered_map<int64_t, uint32_t> col;
-  col.reserve(P.m * 2);
-  for (uint32_t c = 0; c < P.m; c++) col.emplace(P.var_of_col[c], c);
+  std::unordered_map<int64_t, uint32_t>& col = P.col_of_var;
+  if (col.empty()) {
+    col.reserve(P.m * 2);
+    for (uint32_t c = 0; c < P.m; c++) col.emplace(P.var_of_col[c], c);
+  }
   z.assign(P.m * 4, 0);
   std::vector<uint8_t> seen(P.m, 0);
   for (uint64_t i = 0; i < n; i++) {
