@@ -95,6 +95,8 @@ def test_prove_through_backend_mirror(cc, shape, emu_lib):
     trapdoor prediction, and verifies; setup output equals the oracle's proving key bytes."""
     cid, c, ctx = cc
     ncons, npub, npriv = shape
+    if cid == 1 and shape in ((5, 2, 1), (30, 1, 2)):
+        pytest.skip("BLS12-381 runs three of the five shapes (the python oracle's 381-bit pairing dominates the CPU tier)")
     oprog, pprog, inputs = rand_prog_pair(c, ncons, npub, npriv, seed=hash(shape) & 0xFFFF, curve_name=c.name)
     ow = oir.execute(c, oprog, inputs)
     from zokrates_b200.ir import Interpreter
