@@ -334,30 +334,55 @@ inline void prog_parse(const uint8_t* data, size_t len, int curve, const uint32_
   }
   // ark symbol table: instance / witness numbering in allocation order (zokrates_ark/src/lib.rs:47-73,94-113)
   static constexpr uint32_t WIT = 0x80000000u;   // symbol = index | WIT for witness variables
-  std::unordered_map<int64_t, uint32_t> sym;
-  sym.reserve(std::min<size_t>((size_t)n_cons, len / 40) + 64);   // a constraint needs at least ~40 bytes: bound the header's claim by the file
+  // Symbol table.  The compiler numbers its variables densely (ids 0 .. #variables, outputs -1, -2, ..), so non-negative ids
+  // below a bound proportional to the file size live in a direct-index vector (one load instead of a hash lookup per term:
+  // the parse of a 2^20-constraint program went from 0.72 s to the number in DESIGN.md §7); anything else goes to the map.
+  struct SymTab {
+    enum : uint32_t { UNSET = 0xFFFFFFFFu };
+    std::vector<uint32_t> dense;
+    std::unordered_map<int64_t, uint32_t> sparse;
+    int64_t dense_cap = 0;
+    uint32_t* find(int64_t id) {
+      if (id >= 0 && id < dense_cap) {
+        if ((size_t)id >= dense.size()) return nullptr;
+        return dense[(size_t)id] == UNSET ? nullptr : &dense[(size_t)id];
+      }
+      auto it = sparse.find(id);
+      return it == sparse.end() ? nullptr : &it->second;
+    }
+    void set(int64_t id, uint32_t v) {
+      if (id >= 0 && id < dense_cap) {
+        if ((size_t)id >= dense.size()) dense.resize(std::max<size_t>((size_t)id + 1, dense.size() * 2), UNSET);
+        dense[(size_t)id] = v;
+      } else {
+        sparse[id] = v;
+      }
+    }
+    bool count(int64_t id) { return find(id) != nullptr; }
+  } sym;
+  sym.dense_cap = (int64_t)std::min<size_t>(len / 8 + 1024, (size_t)1 << 28);   // a variable that occurs costs >= 8 bytes of file
   std::vector<int64_t> inst, wit;
-  sym[0] = 0;
+  sym.set(0, 0);
   inst.push_back(0);
   for (size_t i = 0; i < P.arg_ids.size(); i++) {
     const int64_t id = P.arg_ids[i];
     if (sym.count(id)) Cbor::bad("duplicate argument");
-    if (P.arg_private[i]) { sym[id] = (uint32_t)wit.size() | WIT; wit.push_back(id); }
-    else { sym[id] = (uint32_t)inst.size(); inst.push_back(id); }
+    if (P.arg_private[i]) { sym.set(id, (uint32_t)wit.size() | WIT); wit.push_back(id); }
+    else { sym.set(id, (uint32_t)inst.size()); inst.push_back(id); }
   }
   std::vector<uint32_t> rsym[3];          // per matrix: symbol of every term (columns are fixed once ni is known)
   for (int k = 0; k < 3; k++) { P.rowptr[k].reserve(std::min<size_t>((size_t)n_cons, len / 40) + 1); P.rowptr[k].push_back(0); }
   auto add_comb = [&](int k, const std::vector<ProgTerm>& terms) {
     for (const ProgTerm& t : terms) {
-      auto it = sym.find(t.var);
+      const uint32_t* it = sym.find(t.var);
       uint32_t s;
-      if (it == sym.end()) {
+      if (!it) {
         if (t.var < 0) { s = (uint32_t)inst.size(); inst.push_back(t.var); }
         else { s = (uint32_t)wit.size() | WIT; wit.push_back(t.var); }
         if (inst.size() >= 0x40000000u || wit.size() >= 0x40000000u) Cbor::bad("too many variables");
-        sym.emplace(t.var, s);
+        sym.set(t.var, s);
       } else {
-        s = it->second;
+        s = *it;
       }
       rsym[k].push_back(s);
       for (int w = 0; w < 4; w++) P.val[k].push_back(le64(t.coeff + 8 * w));
@@ -466,14 +491,14 @@ inline void prog_parse(const uint8_t* data, size_t len, int curve, const uint32_
   P.var_of_col = inst;
   P.var_of_col.insert(P.var_of_col.end(), wit.begin(), wit.end());
   auto col_of = [&](int64_t v) -> uint32_t {
-    auto it = sym.find(v);
-    if (it == sym.end()) {   // only directives touch it: an extra column behind the R1CS ones
+    const uint32_t* it = sym.find(v);
+    if (!it) {   // only directives touch it: an extra column behind the R1CS ones
       const uint32_t cidx = (uint32_t)P.var_of_col.size();
-      sym.emplace(v, cidx | 0x40000000u);
+      sym.set(v, cidx | 0x40000000u);
       P.var_of_col.push_back(v);
       return cidx;
     }
-    const uint32_t s = it->second;
+    const uint32_t s = *it;
     if (s & 0x40000000u) return s & ~0x40000000u;
     return (s & WIT) ? (uint32_t)P.ni + (s & ~WIT) : s;
   };
