@@ -115,6 +115,22 @@ class TestRng:
         out = [(x + y) & 0xFFFFFFFF for x, y in zip(s, init)]
         assert out[:4] == [0xE4E7F110, 0x15593BD1, 0x1FDD0F50, 0xC47120A3]
 
+    def test_chacha12_published_vector(self):
+        """ChaCha12, 256-bit all-zero key, zero nonce / counter: the published keystream block (draft-strombergson-chacha-test-
+        vectors-01, TC1, 12 rounds — the vector rand_chacha's own ChaCha12 tests use).  Pins the 12-round core itself, oracle and
+        product, to something outside this repository; the word order of `next_u32` (little-endian words in state order) with it."""
+        want = bytes.fromhex("9bf49a6a0755f953811fce125f2683d50429c3bb49e074147e0089a52eae155f"
+                             "0564f879d27ae3c02ce82834acfa8c793a629f2ca0de6919610be82f411326be")
+        from zokrates_b200.rng import StdRng
+        for rng in (ark.ChaCha12Rng(bytes(32)), StdRng(bytes(32))):
+            assert b"".join(rng.next_u32().to_bytes(4, "little") for _ in range(16)) == want
+
+    def test_blake2b_seed_published_vector(self):
+        """get_rng_from_entropy hashes the entropy with Blake2b-512 (rng.rs:5-20); hashlib's implementation against the RFC 7693
+        appendix A vector ("abc")."""
+        import hashlib
+        assert hashlib.blake2b(b"abc", digest_size=64).hexdigest().startswith("ba80a53f981c4d0d6a2797b69f12f6e94c212f14685ac4b74b12bb6fdbffa2d1")
+
     def test_fr_rand_in_range_and_deterministic(self):
         for c in (BN254, BLS12_381):
             a = ark.fr_rand(c, ark.rng_from_entropy("entropy"))
