@@ -50,8 +50,23 @@ def test_unsatisfied_and_errors_emu(emu_lib):
         witness_gpu.generate_witness(prog, [3, 10], lib=emu_lib)
     with pytest.raises(ValueError, match="WrongInputCount"):
         witness_gpu.generate_witness(prog, [3], lib=emu_lib)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ZkbError, match="signature"):          # a malformed directive is refused when the program is loaded
         witness_gpu.generate_witness(Prog([Parameter.private_(x)], 0, [Directive([], [y], "Xor")]), [1], lib=emu_lib)
+
+
+def test_programs_with_directives_route_through_the_front_door_emu(emu_lib):
+    """generate_witness / prove_from_inputs on programs WITH solver directives: same witness as the interpreter mirror, same proof
+    as interpreter + B200.generate_proof."""
+    import io
+    from tests.test_prog_native import solver_program
+    from zokrates_b200 import backend, rng as prng
+    prog, inputs = solver_program("bn128", 8), [201, 77, 5]
+    ref = ir.Interpreter().execute(prog, inputs)
+    assert witness_gpu.generate_witness(prog, inputs, lib=emu_lib).values == ref.values
+    kp = backend.B200.setup(prog, [3, 5, 7, 11, 13, 17, 19], lib=emu_lib)
+    want = backend.B200.generate_proof(prog, ref, io.BytesIO(kp.pk), prng.get_rng_from_entropy("d"), lib=emu_lib)
+    got = witness_gpu.prove_from_inputs(prog, inputs, io.BytesIO(kp.pk), prng.get_rng_from_entropy("d"), lib=emu_lib)
+    assert got.to_tagged_json() == want.to_tagged_json()
 
 
 def test_inputs_to_proof_without_leaving_the_device_emu(emu_lib):

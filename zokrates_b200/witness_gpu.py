@@ -5,9 +5,10 @@
 variable with coefficient one that has no value yet ASSIGNS it the value of the quadratic side, every other constraint is
 CHECKED (`Error::UnsatisfiedConstraint`), directives call a solver.  The assignments form a dependency DAG; all statements
 of one depth are independent, so the device evaluates the program level by level (`zkb_witness_eval`, one thread per
-statement).  This module does the host part: it derives the levels from the R1CS rows (same rule, same statement order
-for ties) and maps the result back to `ir.Witness`.  Directives have no device path — programs that use solvers stay with
-`ir.Interpreter`, as they stay on the host in the reference.
+statement).  This module does the host part for constraint-only programs: it derives the levels from the R1CS rows (same rule,
+same statement order for ties) and maps the result back to `ir.Witness`.  Programs with solver directives go through the
+native front door (`zkb_prog_load` / `zkb_prog_compute_witness`: the library schedules constraints AND directives by level and
+runs the solver kernels of csrc/solvers.cuh) — `generate_witness` and `prove_from_inputs` route them there.
 """
 from __future__ import annotations
 
@@ -169,7 +170,7 @@ def generate_witness(prog: Prog, inputs: Sequence[int], ctx=None, lib=None) -> W
     if len(inputs) != len(prog.arguments):
         raise ValueError(f"WrongInputCount: expected {len(prog.arguments)}, received {len(inputs)}")
     if any(isinstance(s, Directive) for s in prog.statements):
-        raise NotImplementedError("solver directives have no device path: use ir.Interpreter")
+        return _generate_witness_native(prog, inputs, ctx, lib)
     r1cs = synthesize(prog)
     cols = {v: i for i, v in enumerate(r1cs.instance_vars)}
     cols.update({v: r1cs.num_instance + i for i, v in enumerate(r1cs.witness_vars)})
@@ -198,6 +199,30 @@ def generate_witness(prog: Prog, inputs: Sequence[int], ctx=None, lib=None) -> W
     return w
 
 
+def _generate_witness_native(prog: Prog, inputs: Sequence[int], ctx=None, lib=None, try_out_of_range: bool = False) -> Witness:
+    """Programs with solver directives: the program file goes to the library, which schedules every statement and runs the
+    solver kernels (same failures: UnsatisfiedConstraint; a solver without a device path — Zir functions — raises
+    NotImplementedError)."""
+    from . import backend, zir
+    from ._lib import ZkbError
+    c = _curve(prog.curve)
+    ctx = ctx or backend.context(c, 0, lib)
+    with ctx.lock:
+        h = ctx.prog_load(zir.write_prog(prog))
+        try:
+            if ctx.prog_info(h)["unsupported_directives"]:
+                raise NotImplementedError("the program calls a solver that has no device path: use ir.Interpreter")
+            try:
+                data = ctx.prog_compute_witness(h, [int(x) % c.r for x in inputs], try_out_of_range)
+            except ZkbError as e:
+                if e.code == 5:
+                    raise UnsatisfiedConstraint(str(e))
+                raise
+        finally:
+            ctx.prog_free(h)
+    return Witness.read(data, c)
+
+
 def prove_from_inputs(prog: Prog, inputs: Sequence[int], proving_key, rng, device: int = 0, lib=None):
     """Inputs -> proof with the assignment never leaving the device between witness generation and proving:
     `zkb_witness_eval` leaves z resident, `zkb_groth16_prove_resident` consumes it (the reference runs
@@ -210,11 +235,34 @@ def prove_from_inputs(prog: Prog, inputs: Sequence[int], proving_key, rng, devic
     c = _curve(prog.curve)
     if len(inputs) != len(prog.arguments):
         raise ValueError(f"WrongInputCount: expected {len(prog.arguments)}, received {len(inputs)}")
-    if any(isinstance(s, Directive) for s in prog.statements):
-        raise NotImplementedError("solver directives have no device path: use ir.Interpreter + B200.generate_proof")
     pk_bytes = proving_key.read() if hasattr(proving_key, "read") else bytes(proving_key)
     r = fr_rand(c, rng)                                      # create_random_proof draws r then s before synthesis
     s = fr_rand(c, rng)
+    if any(isinstance(st, Directive) for st in prog.statements):
+        # native front door: witness generation (solver kernels included) leaves z resident in the program's R1CS
+        from . import zir
+        ctx = backend.context(c, device, lib)
+        with ctx.lock:
+            h = ctx.prog_load(zir.write_prog(prog))
+            pk_h = None
+            try:
+                info = ctx.prog_info(h)
+                if info["unsupported_directives"]:
+                    raise NotImplementedError("the program calls a solver that has no device path")
+                try:
+                    ctx.prog_compute_witness(h, [int(x) % c.r for x in inputs])
+                except ZkbError as e:
+                    if e.code == 5:
+                        raise UnsatisfiedConstraint(str(e))
+                    raise
+                public = ctx.prog_public_inputs(h)
+                pk_h = ctx.pk_load(pk_bytes, 0, 1)
+                raw = ctx.prove_resident(pk_h, info["r1cs"], r, s)
+            finally:
+                if pk_h:
+                    ctx.pk_free(pk_h)
+                ctx.prog_free(h)
+        return Proof.from_raw(c, raw, public)
     r1cs = synthesize(prog)
     cols = {v: i for i, v in enumerate(r1cs.instance_vars)}
     cols.update({v: r1cs.num_instance + i for i, v in enumerate(r1cs.witness_vars)})
